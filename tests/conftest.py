@@ -1,0 +1,42 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "quantum-targeted-energy-transfer_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    # GPU tests are selected with `-m gpu`; if someone runs the whole suite on a CPU-only box
+    # they are skipped rather than failed.
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "reference_golden.json")) as fh:
+        return json.load(fh)
+
+
+def make_const(N, omegas=(-3, 3), coupling=1, max_t=25, timesteps=30):
+    return {"max_N": N, "sites": len(omegas), "max_t": max_t, "omegas": list(omegas),
+            "chis": [0] * len(omegas), "coupling": coupling, "timesteps": timesteps}
