@@ -1,0 +1,321 @@
+#!/usr/bin/env python3
+"""bench.py -- loss+grad evaluations / second of the QTET hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload dimer20|trimer10|dimer100|dimer4]
+
+A "step" is one pass of the hot path (H build -> eigendecomposition -> <n(t)> on the time grid -> loss ->
+gradient) over one batch of synthetic parameter points.  Default workload = BASELINE.json configs[1]:
+dimer N=20, the 1024 x 1024 (chi_D, chi_A) grid on [-10, 10]^2 (B = 1,048,576 points per GPU).
+For N > 1 (torchrun, one rank per GPU) every rank evaluates its own B points (weak scaling; the points of
+rank r are the grid shifted by r * 1e-3 so that no two ranks do identical work); there is no data-path
+collective -- only the barrier and the max-over-ranks of the timing.
+
+Prints ONE JSON line (rank 0).  Keys: the base contract + "roofline", "cpu_baseline", "e2e", "clocks",
+"gpu_launches".  `--impl reference` times the CPU restatement of the reference (oracle/, numpy + LAPACK
+over all host cores) on a bounded sample of the same workload: the real reference needs TensorFlow,
+which cannot be installed in this image.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "quantum-targeted-energy-transfer_b200"))
+
+WORKLOADS = {
+    # name: (max_N, omegas, grid/random spec)
+    "dimer20": dict(max_N=20, omegas=[-3, 3], kind="grid", side=1024, label="dimer N=20, 1024x1024 (chi_D,chi_A) grid on [-10,10]^2"),
+    "dimer4": dict(max_N=4, omegas=[-3, 3], kind="grid", side=1024, label="dimer N=4, 1024x1024 grid on [-10,10]^2"),
+    "dimer100": dict(max_N=100, omegas=[-3, 3], kind="random", B=1 << 14, label="dimer N=100, 2^14 uniform points in [-10,10]^2 (seed 0)"),
+    "trimer10": dict(max_N=10, omegas=[-3, 3, 3], kind="random", B=1 << 16, label="trimer N=10, 2^16 uniform points in [-10,10]^3 (seed 0)"),
+}
+
+
+def make_const(w):
+    return {"max_N": w["max_N"], "sites": len(w["omegas"]), "max_t": 25, "omegas": w["omegas"],
+            "chis": [0] * len(w["omegas"]), "coupling": 1, "timesteps": 30}
+
+
+def make_points(w, rank=0):
+    f = len(w["omegas"])
+    if w["kind"] == "grid":
+        ax = np.linspace(-10, 10, w["side"])
+        xd, xa = np.meshgrid(ax, ax, indexing="ij")            # chi_D slowest
+        pts = np.stack([xd.ravel(), xa.ravel()], axis=1)
+    else:
+        pts = np.random.default_rng(0).uniform(-10, 10, (w["B"], f))
+    return np.ascontiguousarray(pts + rank * 1e-3)
+
+
+def algorithmic_flops(d, T, tridiagonal):
+    # F = F_eigh + 4 T d^2 + 4 d^3 ; F_eigh = 6 d^3 (tridiagonal) / 9 d^3 (dense)
+    return (6.0 if tridiagonal else 9.0) * d ** 3 + 4.0 * T * d ** 2 + 4.0 * d ** 3
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU restatement of the reference (oracle/) on all host cores -- the baseline, never the product
+# --------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    const, pts, site = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from oracle import qtet_oracle as O
+    out = []
+    for lo in range(0, len(pts), 2048):
+        out.append(O.loss_grad_batch(const, pts[lo:lo + 2048], site)[0])
+    return float(np.sum(np.concatenate(out)))
+
+
+def cpu_rate(const, pts, cores, seconds_target=12.0):
+    """evaluations/s of the vectorised numpy restatement over `cores` processes on a bounded sample."""
+    import multiprocessing as mp
+    site = const["sites"] - 1
+    ctx = mp.get_context("fork")
+    # calibrate on one core
+    probe = pts[:min(len(pts), 256)]
+    t0 = time.perf_counter(); _cpu_worker((const, probe, site)); t_probe = time.perf_counter() - t0
+    per_core = len(probe) / t_probe
+    n = int(min(len(pts), max(cores * 256, per_core * cores * seconds_target)))
+    n -= n % cores
+    chunks = np.array_split(pts[:n], cores)
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(const, c[:8], site) for c in chunks])        # warm the workers
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, [(const, c, site) for c in chunks])
+        dt = time.perf_counter() - t0
+    return n / dt, n, dt
+
+
+def run_reference_arm(args, w, const):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    pts = make_points(w)
+    rng = np.random.default_rng(1)
+    pts = pts[rng.permutation(len(pts))]              # unbiased sample of the grid
+    rates, used = [], 0
+    per_step_seconds = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    for i in range(args.warmup + args.steps):
+        r, n, dt = cpu_rate(const, pts, cores, seconds_target=per_step_seconds)
+        if i >= args.warmup:
+            rates.append(r); used = n
+    value = float(np.mean(rates))
+    line = {"impl": "reference", "metric": "loss+grad evals/sec", "value": value, "unit": "evals/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * used / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["label"], "sample_points_per_step": used,
+                       "note": "CPU restatement of the reference formulas (oracle/qtet_oracle.py: batched LAPACK eigh + "
+                               "analytic gradient) on all host cores; the TensorFlow reference cannot be installed here"},
+            "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
+                             "sample": f"{used} random points of the workload per step"},
+            "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="dimer20", choices=sorted(WORKLOADS))
+    ap.add_argument("--path", default="auto", choices=["auto", "generic", "split"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--points", type=int, default=0, help="override the number of points per GPU (debug)")
+    args = ap.parse_args()
+    if args.impl == "ours":
+        args.warmup = max(args.warmup, 3)          # timing rule: at least 3 untimed warm-up steps
+    w = WORKLOADS[args.workload]
+    const = make_const(w)
+    if args.impl == "reference":
+        run_reference_arm(args, w, const)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from tet import _native
+
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the QTET B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    prob = _native.Problem.from_const(const, device=local)
+    if args.path != "auto":
+        prob.set_path({"generic": _native.QTET_PATH_GENERIC, "split": _native.QTET_PATH_SPLIT}[args.path])
+    path_name = {1: "generic", 2: "split"}[prob.get_path()]
+    pts_host = make_points(w, rank)
+    if args.points:
+        pts_host = pts_host[:args.points]
+    B, f = pts_host.shape
+    chis = torch.from_numpy(pts_host).to(dev)
+    loss = torch.empty(B, dtype=torch.float64, device=dev)
+    grad = torch.empty(B, f, dtype=torch.float64, device=dev)
+    tst = torch.empty(B, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def step():
+        prob.loss_grad(chis, out=(loss, grad, tst))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = _native.launch_count()
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()                        # L2 flush between timed iterations (outside the event pair)
+        ev[i][0].record()
+        step()
+        ev[i][1].record()
+    barrier()
+    launches = _native.launch_count() - launches0
+    clocks = sampler.stop()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(ms))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = world * B * args.steps / (total_ms * 1e-3)
+
+    # ---- end-to-end through the C ABI with HOST buffers (pinned), H2D + kernels + D2H inside the call
+    h_chis = torch.from_numpy(pts_host).pin_memory()
+    h_loss = torch.empty(B, dtype=torch.float64).pin_memory()
+    h_grad = torch.empty(B, f, dtype=torch.float64).pin_memory()
+    h_ts = torch.empty(B, dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        rc = _native.lib.qtet_loss_grad_host(prob._h, h_chis.data_ptr(), B, f - 1, h_loss.data_ptr(),
+                                             h_grad.data_ptr(), h_ts.data_ptr())
+        if rc:
+            raise RuntimeError(_native.lib.qtet_last_error().decode())
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * B * args.steps / e2e_s
+    checksum = float(h_loss.sum())
+
+    if rank == 0:
+        d = prob.dim
+        F = algorithmic_flops(d, const["timesteps"], tridiagonal=(f == 2))
+        try:
+            peak = _native.fp64_peak_tflops(local, 0.5)
+        except Exception:
+            peak = None
+        per_gpu_rate = B * args.steps / (total_ms * 1e-3)
+        achieved = per_gpu_rate * F / 1e12
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+        except Exception:
+            pass
+        hbm_bytes = (8 * f) + 8 * (1 + f) + 4
+        roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": (achieved / peak) if peak else None, "traffic": None,
+                    "flops_per_eval": F,
+                    "peak_source": "FP64 DFMA micro-benchmark run inside this bench (MEASURED_PEAKS.json has no FP64 figure)",
+                    "kernel_path": path_name,
+                    "hbm": {"algorithmic_bytes_per_eval": hbm_bytes, "achieved_GBps": per_gpu_rate * hbm_bytes / 1e9,
+                            "peak_GBps": peaks.get("hbm_gbs"), "frac": (per_gpu_rate * hbm_bytes / 1e9 / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None}}
+        cpu = None
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            sample = pts_host[np.random.default_rng(1).permutation(B)]
+            r, n, dt = cpu_rate(const, sample, cores, seconds_target=12.0)
+            cpu = {"value": r, "unit": "evals/s", "cores": cores, "kind": "port",
+                   "sample": f"{n} random points of the workload, {dt:.1f} s wall on {cores} processes "
+                             "(oracle/qtet_oracle.py: batched LAPACK eigh + analytic gradient)"}
+        line = {"metric": "loss+grad evals/sec", "value": value, "unit": "evals/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": w["label"], "points_per_gpu": B, "fock_dim": d, "timesteps": const["timesteps"],
+                           "target_site": "acceptor", "kernel_path": path_name,
+                           "l2": "256 MiB buffer written between timed iterations (L2 flush)"},
+                "roofline": roofline, "cpu_baseline": cpu,
+                "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(B * f * 8),
+                        "d2h_bytes_per_step": int(B * (8 + 8 * f + 4)), "checksum_loss_sum": checksum},
+                "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

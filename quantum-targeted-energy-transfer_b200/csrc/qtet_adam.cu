@@ -1,0 +1,302 @@
+// Batched per-guess optimiser (Optimizer.train, Optimizer.py:99-242), arg-min over guesses
+// (solver_mp.py:182-184) and the FP64 peak micro-benchmark.
+//
+// One thread per initial guess carries the whole per-guess state of the reference loop: Keras Adam
+// moments, best-so-far tracking, the step-revert rule, the lr drop at loss<=0.1, the TET break and the
+// ">2 sub-tol moves" stop.  Guesses that stopped are compacted away so that the loss+grad kernels only
+// ever see live guesses (ragged convergence).
+#include <cmath>
+#include <limits>
+
+#include "qtet_common.cuh"
+
+namespace qtet {
+
+namespace {
+
+struct AdamArgs {
+    int f;
+    long long n_active;
+    const int* active;        // [n_active] guess ids
+    const double* xc;         // [n_active, f] compacted variables the loss/grad was evaluated at
+    const double* loss;       // [n_active]
+    const double* grad;       // [n_active, f]
+    double* x;                // [B, f]
+    double* m; double* v; double* vhat;   // [B, f]
+    double* lr;               // [B]
+    double* last_loss;        // [B]  mylosses[epoch]
+    double* min_loss;         // [B]  min(mylosses[:epoch+1])
+    double* best_vars;        // [B, f]
+    int* err_count;           // [B, f]
+    int* alive;               // [B]
+    int* epochs;              // [B]
+    unsigned train_mask;
+    double beta_1, beta_2, epsilon, tol, s2, s1;
+    int amsgrad;
+    int epoch;
+    long long B;
+    double* loss_hist;        // [iterations, B] or null
+    double* var_hist;         // [iterations/10, B, f] or null
+};
+
+// Optimizer.py:146-224, one epoch for every live guess.
+__global__ void adam_step_kernel(AdamArgs a) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= a.n_active) return;
+    const int b = a.active[i];
+    const int f = a.f;
+    const double L = a.loss[i];
+    double lr = a.lr[b];
+    if (L <= 0.1) lr = 0.0001;                               // :165-166
+    a.lr[b] = lr;
+    if (a.loss_hist) a.loss_hist[(long long)a.epoch * a.B + b] = L;      // :169
+    const double last = a.last_loss[b];
+    double mn = a.min_loss[b];
+    if (L < mn) {                                            // :172-175 (before the step)
+        for (int k = 0; k < f; ++k) a.best_vars[(long long)b * f + k] = a.xc[i * f + k];
+        mn = L;
+    }
+    a.min_loss[b] = mn;
+    a.last_loss[b] = L;
+    const double alpha = lr * a.s2 / a.s1;                   // Keras Adam, t = epoch+1
+    bool stop = false;
+    const bool revert = (L - last >= 0.5) && (L >= 0.5);     // :184
+    bool counted_stop = false;
+    for (int k = 0; k < f; ++k) {
+        const long long o = (long long)b * f + k;
+        const double x0 = a.xc[i * f + k];
+        double x1 = x0;
+        if ((a.train_mask >> k) & 1u) {
+            const double g = a.grad[i * f + k];
+            double m = a.m[o], v = a.v[o];
+            m += (g - m) * (1.0 - a.beta_1);
+            v += (g * g - v) * (1.0 - a.beta_2);
+            a.m[o] = m; a.v[o] = v;
+            double denom_v = v;
+            if (a.amsgrad) { double vh = fmax(a.vhat[o], v); a.vhat[o] = vh; denom_v = vh; }
+            x1 = x0 - alpha * m / (sqrt(denom_v) + a.epsilon);
+            const double err = fabs(x1 - x0);                // :181
+            if (!counted_stop && err < a.tol) {              // :202-206 (first offending site returns)
+                const int c = a.err_count[o] + 1;
+                a.err_count[o] = c;
+                if (c > 2) counted_stop = true;
+            }
+        }
+        a.x[o] = revert ? x0 : x1;                           // :184-186
+    }
+    if (a.var_hist && ((a.epoch + 1) % 10 == 0)) {           // :189-192
+        const long long slot = (a.epoch + 1) / 10 - 1;
+        for (int k = 0; k < f; ++k) a.var_hist[(slot * a.B + b) * f + k] = a.x[(long long)b * f + k];
+    }
+    if (fabs(L) < 0.1) stop = true;                          // :195-196
+    else if (counted_stop) stop = true;
+    a.epochs[b] = a.epoch + 1;
+    if (stop) a.alive[b] = 0;
+}
+
+// Build the compacted list of live guesses and gather their variables.
+__global__ void compact_kernel(const int* alive, long long B, int* active, int* n_active) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const bool live = (b < B) && alive[b];
+    const unsigned ballot = __ballot_sync(0xffffffffu, live);
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0 && ballot) base = atomicAdd(n_active, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (live) active[base + __popc(ballot & ((1u << lane) - 1u))] = (int)b;
+}
+
+__global__ void gather_kernel(const int* active, long long n, int f, const double* x, double* xc) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n * f) return;
+    const long long r = i / f;
+    const int k = (int)(i - r * f);
+    xc[i] = x[(long long)active[r] * f + k];
+}
+
+__global__ void adam_init_kernel(long long B, int f, double N, double lr, double* m, double* v, double* vhat,
+                                 double* lrv, double* last, double* mn, double* best, int* err, int* alive, int* epochs) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    for (int k = 0; k < f; ++k) {
+        const long long o = b * f + k;
+        m[o] = 0.0; v[o] = 0.0; vhat[o] = 0.0; best[o] = 0.0; err[o] = 0;      // Optimizer.py:133, 143
+    }
+    lrv[b] = lr; last[b] = N; mn[b] = N; alive[b] = 1; epochs[b] = 0;           // :135-138
+}
+
+__global__ void fill_nan_kernel(double* p, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = __longlong_as_double(0x7ff8000000000000LL);
+}
+
+// ---------------------------------------------------------------------------------- argmin
+__global__ void argmin_kernel(const double* v, long long B, double* min_out, long long* idx_out) {
+    __shared__ double sv[32];
+    __shared__ long long si[32];
+    double bv = __longlong_as_double(0x7ff0000000000000LL);
+    long long bi = B;
+    for (long long i = threadIdx.x; i < B; i += blockDim.x) {
+        const double x = v[i];
+        if (x < bv) { bv = x; bi = i; }         // strided scan keeps the smallest index per thread
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            if (sv[w] < bv || (sv[w] == bv && si[w] < bi)) { bv = sv[w]; bi = si[w]; }
+        *min_out = bv;
+        *idx_out = (bi == B) ? 0 : bi;
+    }
+}
+
+// ---------------------------------------------------------------------------------- FP64 peak
+__global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace
+
+int launch_argmin(const double* v, int64_t B, double* min_out, int64_t* idx_out, cudaStream_t st) {
+    argmin_kernel<<<1, 1024, 0, st>>>(v, (long long)B, min_out, (long long*)idx_out);
+    count_launch();
+    QTET_CUDA(cudaGetLastError());
+    return QTET_OK;
+}
+
+}  // namespace qtet
+
+using namespace qtet;
+
+extern "C" int qtet_adam_run(qtet_problem* p, double* chis_dev, int64_t B, int target_site,
+                             const int32_t* train_mask_host, int iterations, double lr, double beta_1,
+                             double beta_2, double epsilon, int amsgrad, double tol,
+                             double* best_vars_dev, double* best_loss_dev, int32_t* epochs_dev,
+                             double* loss_hist_dev, double* var_hist_dev, void* stream) {
+    if (!p || !chis_dev || !train_mask_host || !best_vars_dev || !best_loss_dev) { set_error("null argument"); return QTET_EINVAL; }
+    if (B <= 0 || B > 0x7fffffffLL) { set_error("batch must be in 1..2^31-1"); return QTET_EINVAL; }
+    if (target_site < 0 || target_site >= p->f) { set_error("target_site out of range"); return QTET_EINVAL; }
+    if (iterations < 0) { set_error("negative iterations"); return QTET_EINVAL; }
+    QTET_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int f = p->f;
+    unsigned mask = 0;
+    for (int k = 0; k < f; ++k) if (train_mask_host[k]) mask |= 1u << k;
+
+    // workspace layout (all on the handle's scratch allocation)
+    const size_t Bf = (size_t)B * f;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_m = take(Bf * 8), o_v = take(Bf * 8), o_vh = take(Bf * 8), o_lr = take(B * 8), o_last = take(B * 8),
+                 o_xc = take(Bf * 8), o_loss = take(B * 8), o_grad = take(Bf * 8), o_err = take(Bf * 4),
+                 o_alive = take(B * 4), o_active = take(B * 4), o_ep = take(B * 4), o_cnt = take(256);
+    int rc = ensure_scratch(p, off);
+    if (rc) return rc;
+    char* base = (char*)p->scratch;
+    double *m = (double*)(base + o_m), *v = (double*)(base + o_v), *vh = (double*)(base + o_vh), *lrv = (double*)(base + o_lr),
+           *last = (double*)(base + o_last), *xc = (double*)(base + o_xc), *lossc = (double*)(base + o_loss),
+           *gradc = (double*)(base + o_grad);
+    int *err = (int*)(base + o_err), *alive = (int*)(base + o_alive), *active = (int*)(base + o_active),
+        *ep = (int*)(base + o_ep), *cnt = (int*)(base + o_cnt);
+    int* h_cnt = nullptr;
+    QTET_CUDA(cudaMallocHost(&h_cnt, sizeof(int)));
+
+    const int TPB = 256;
+    const unsigned gB = (unsigned)((B + TPB - 1) / TPB);
+    adam_init_kernel<<<gB, TPB, 0, st>>>((long long)B, f, (double)p->N, lr, m, v, vh, lrv, last, best_loss_dev, best_vars_dev, err, alive, ep);
+    count_launch();
+    if (loss_hist_dev && iterations > 0) {
+        const long long n = (long long)iterations * B;
+        fill_nan_kernel<<<(unsigned)((n + TPB - 1) / TPB), TPB, 0, st>>>(loss_hist_dev, n);
+        count_launch();
+    }
+    if (var_hist_dev && iterations >= 10) {
+        const long long n = (long long)(iterations / 10) * B * f;
+        fill_nan_kernel<<<(unsigned)((n + TPB - 1) / TPB), TPB, 0, st>>>(var_hist_dev, n);
+        count_launch();
+    }
+    int epoch = 0;
+    long long n_active = B;
+    for (; epoch < iterations; ++epoch) {
+        // live list (compaction) -- sync point: the host needs the count to size the launches
+        cudaMemsetAsync(cnt, 0, sizeof(int), st);
+        compact_kernel<<<gB, TPB, 0, st>>>(alive, (long long)B, active, cnt);
+        count_launch();
+        cudaMemcpyAsync(h_cnt, cnt, sizeof(int), cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { cudaFreeHost(h_cnt); return cuda_fail(e, "adam: sync"); }
+        n_active = *h_cnt;
+        if (n_active == 0) break;
+        const long long nf = n_active * f;
+        gather_kernel<<<(unsigned)((nf + TPB - 1) / TPB), TPB, 0, st>>>(active, n_active, f, chis_dev, xc);
+        count_launch();
+        rc = loss_grad_dispatch(p, xc, n_active, target_site, lossc, gradc, nullptr, nullptr, st);
+        if (rc) { cudaFreeHost(h_cnt); return rc; }
+        AdamArgs a;
+        a.f = f; a.n_active = n_active; a.active = active; a.xc = xc; a.loss = lossc; a.grad = gradc;
+        a.x = chis_dev; a.m = m; a.v = v; a.vhat = vh; a.lr = lrv; a.last_loss = last; a.min_loss = best_loss_dev;
+        a.best_vars = best_vars_dev; a.err_count = err; a.alive = alive; a.epochs = ep; a.train_mask = mask;
+        a.beta_1 = beta_1; a.beta_2 = beta_2; a.epsilon = epsilon; a.tol = tol;
+        const int t = epoch + 1;
+        a.s2 = std::sqrt(1.0 - std::pow(beta_2, (double)t));
+        a.s1 = 1.0 - std::pow(beta_1, (double)t);
+        a.amsgrad = amsgrad; a.epoch = epoch; a.B = B; a.loss_hist = loss_hist_dev; a.var_hist = var_hist_dev;
+        adam_step_kernel<<<(unsigned)((n_active + TPB - 1) / TPB), TPB, 0, st>>>(a);
+        count_launch();
+    }
+    if (epochs_dev) cudaMemcpyAsync(epochs_dev, ep, (size_t)B * 4, cudaMemcpyDeviceToDevice, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFreeHost(h_cnt);
+    if (e != cudaSuccess) return cuda_fail(e, "adam: final sync");
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "adam: kernel");
+    return epoch;
+}
+
+extern "C" int qtet_fp64_peak(int device, double seconds_budget, double* tflops_out) {
+    if (!tflops_out) { set_error("null argument"); return QTET_EINVAL; }
+    QTET_CUDA(cudaSetDevice(device));
+    int sms = 0;
+    QTET_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    double* out = nullptr;
+    const int blocks = sms * 8, threads = 256;
+    QTET_CUDA(cudaMalloc(&out, (size_t)blocks * threads * 8));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int iters = 2000;
+    double best = 0.0, spent = 0.0;
+    for (int rep = 0; rep < 50 && spent < seconds_budget; ++rep) {
+        cudaEventRecord(e0);
+        dfma_peak_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-7);
+        count_launch();
+        cudaEventRecord(e1);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) { cudaFree(out); return cuda_fail(e, "fp64 peak"); }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 64.0 * (double)iters * blocks * threads;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+        spent += ms * 1e-3;
+        if (ms < 20.f) iters *= 2;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops_out = best;
+    return QTET_OK;
+}

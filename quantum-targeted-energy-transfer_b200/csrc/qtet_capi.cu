@@ -1,0 +1,274 @@
+// C ABI of libqtet_b200.so (see include/qtet.h).  Host-side problem setup + dispatch.
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <new>
+
+#include "qtet_common.cuh"
+
+namespace qtet {
+
+static thread_local std::string g_last_error;
+static std::atomic<long long> g_launches{0};
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+int cuda_fail(cudaError_t e, const char* what) {
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return QTET_ECUDA;
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// Descending-lexicographic enumeration = the order Loss.derive produces (HamiltonianLoss.py:62-110).
+static void enumerate_states(int N, int f, std::vector<int>& cur, int k, int remaining,
+                             std::vector<std::vector<int>>& out) {
+    if (k == f - 1) {
+        cur[k] = remaining;
+        out.push_back(cur);
+        return;
+    }
+    for (int n = remaining; n >= 0; --n) {
+        cur[k] = n;
+        enumerate_states(N, f, cur, k + 1, remaining - n, out);
+    }
+}
+
+int ensure_scratch(qtet_problem* p, size_t bytes) {
+    if (bytes <= p->scratch_bytes) return QTET_OK;
+    if (p->scratch) cudaFree(p->scratch);
+    p->scratch = nullptr;
+    p->scratch_bytes = 0;
+    size_t want = bytes + bytes / 4 + 4096;
+    cudaError_t e = cudaMalloc(&p->scratch, want);
+    if (e != cudaSuccess) { set_error("cudaMalloc(scratch) failed"); cudaGetLastError(); return QTET_ENOMEM; }
+    p->scratch_bytes = want;
+    return QTET_OK;
+}
+
+int loss_grad_dispatch(qtet_problem* p, const double* chis, int64_t B, int site, double* loss,
+                       double* grad, int32_t* tstar, double* trace, cudaStream_t st) {
+    if (p->path == QTET_PATH_SPLIT)
+        return launch_split(p->view, &p->split_ws, chis, B, site, loss, grad, tstar, trace, st);
+    return launch_generic(p->view, chis, B, site, loss, grad, tstar, trace, st);
+}
+
+}  // namespace qtet
+
+using namespace qtet;
+
+extern "C" {
+
+int qtet_problem_create(int max_N, int sites, const double* omegas, double coupling, double max_t,
+                        int timesteps, int device, qtet_problem** out) {
+    if (!out) { set_error("out is NULL"); return QTET_EINVAL; }
+    *out = nullptr;
+    if (max_N < 1 || sites < 2 || !omegas || timesteps < 1) {
+        set_error("need max_N >= 1, sites >= 2, omegas != NULL, timesteps >= 1");
+        return QTET_EINVAL;
+    }
+    if (sites > 8) { set_error("at most 8 sites are supported"); return QTET_EUNSUPPORTED; }
+    std::vector<std::vector<int>> st;
+    {
+        // guard the enumeration size before doing it
+        double dim = 1.0;
+        for (int i = 1; i <= sites - 1; ++i) dim = dim * (max_N + i) / i;
+        if (dim > 4096) { set_error("Fock dimension too large"); return QTET_EUNSUPPORTED; }
+        std::vector<int> cur(sites, 0);
+        enumerate_states(max_N, sites, cur, 0, max_N, st);
+    }
+    const int d = (int)st.size();
+    QTET_CUDA(cudaSetDevice(device));
+
+    qtet_problem* p = new (std::nothrow) qtet_problem();
+    if (!p) { set_error("out of host memory"); return QTET_ENOMEM; }
+    p->N = max_N; p->f = sites; p->d = d; p->T = timesteps; p->device = device;
+    p->coupling = coupling; p->max_t = max_t;
+    p->omegas.assign(omegas, omegas + sites);
+    p->states.resize((size_t)d * sites);
+    std::map<std::vector<int>, int> index;
+    for (int m = 0; m < d; ++m) {
+        index[st[m]] = m;
+        for (int k = 0; k < sites; ++k) p->states[(size_t)m * sites + k] = st[m][k];
+    }
+    // hopping part (HamiltonianLoss.py:136-163); the reference locates the neighbour state through
+    // a float hash + searchsorted (:112-121), an exact map lookup gives the same index.
+    std::vector<double> dense((size_t)d * d, 0.0);
+    int bandwidth = 0;
+    for (int m = 0; m < d; ++m) {
+        for (int k = 0; k < sites - 1; ++k) {
+            const int nk = st[m][k], nk1 = st[m][k + 1];
+            if (nk != 0) {
+                std::vector<int> t = st[m]; t[k] -= 1; t[k + 1] += 1;
+                const int n = index[t];
+                dense[(size_t)n * d + m] -= coupling * std::sqrt((double)(nk1 + 1) * nk);
+                bandwidth = std::max(bandwidth, std::abs(n - m));
+            }
+            if (nk1 != 0) {
+                std::vector<int> t = st[m]; t[k] += 1; t[k + 1] -= 1;
+                const int n = index[t];
+                dense[(size_t)n * d + m] -= coupling * std::sqrt((double)nk1 * (nk + 1));
+                bandwidth = std::max(bandwidth, std::abs(n - m));
+            }
+        }
+    }
+    p->tridiag = bandwidth <= 1;
+    // time grid = numpy.linspace(0, max_t, T): k*step, last sample exactly max_t
+    p->tgrid.resize(timesteps);
+    if (timesteps == 1) p->tgrid[0] = 0.0;
+    else {
+        const double step = max_t / (double)(timesteps - 1);
+        for (int k = 0; k < timesteps; ++k) p->tgrid[k] = (double)k * step;
+        p->tgrid[timesteps - 1] = max_t;
+    }
+    // pack constants
+    std::vector<double> blob;
+    auto push = [&](const std::vector<double>& v) { size_t o = blob.size(); blob.insert(blob.end(), v.begin(), v.end()); return o; };
+    std::vector<double> lin(d), quad((size_t)d * sites);
+    for (int m = 0; m < d; ++m) {
+        double acc = 0.0;
+        for (int k = 0; k < sites; ++k) {
+            const double n = st[m][k];
+            acc += omegas[k] * n;
+            quad[(size_t)m * sites + k] = 0.5 * n * n;
+        }
+        lin[m] = acc;
+    }
+    std::vector<double> offd;
+    if (p->tridiag) {
+        offd.resize(d > 1 ? d - 1 : 1, 0.0);
+        for (int m = 0; m + 1 < d; ++m) offd[m] = dense[(size_t)(m + 1) * d + m];
+    } else {
+        offd = dense;
+    }
+    const size_t o_lin = push(lin), o_quad = push(quad), o_occ = push(p->states), o_off = push(offd),
+                 o_t = push(p->tgrid), o_om = push(p->omegas);
+    cudaError_t e = cudaMalloc(&p->dev_blob, blob.size() * sizeof(double));
+    if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaMalloc(constants)"); }
+    e = cudaMemcpy(p->dev_blob, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(p->dev_blob); delete p; return cuda_fail(e, "cudaMemcpy(constants)"); }
+    ProblemView& v = p->view;
+    v.N = max_N; v.f = sites; v.d = d; v.T = timesteps; v.tridiag = p->tridiag ? 1 : 0; v.max_t = max_t;
+    v.lin = p->dev_blob + o_lin; v.quad = p->dev_blob + o_quad; v.occ = p->dev_blob + o_occ;
+    v.offd = p->dev_blob + o_off; v.tgrid = p->dev_blob + o_t; v.omegas = p->dev_blob + o_om;
+    p->path = split_eligible(v) ? QTET_PATH_SPLIT : QTET_PATH_GENERIC;
+    *out = p;
+    return QTET_OK;
+}
+
+void qtet_problem_destroy(qtet_problem* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    if (p->dev_blob) cudaFree(p->dev_blob);
+    if (p->scratch) cudaFree(p->scratch);
+    split_workspace_free(p->split_ws);
+    delete p;
+}
+
+int qtet_problem_dim(const qtet_problem* p) { return p ? p->d : QTET_EINVAL; }
+
+int qtet_problem_states(const qtet_problem* p, double* states_host) {
+    if (!p || !states_host) { set_error("null argument"); return QTET_EINVAL; }
+    std::memcpy(states_host, p->states.data(), p->states.size() * sizeof(double));
+    return QTET_OK;
+}
+
+int qtet_problem_time_grid(const qtet_problem* p, double* t_host) {
+    if (!p || !t_host) { set_error("null argument"); return QTET_EINVAL; }
+    std::memcpy(t_host, p->tgrid.data(), p->tgrid.size() * sizeof(double));
+    return QTET_OK;
+}
+
+int qtet_set_path(qtet_problem* p, int path) {
+    if (!p) { set_error("null handle"); return QTET_EINVAL; }
+    if (path == QTET_PATH_AUTO) { p->path = split_eligible(p->view) ? QTET_PATH_SPLIT : QTET_PATH_GENERIC; return QTET_OK; }
+    if (path == QTET_PATH_GENERIC) { p->path = path; return QTET_OK; }
+    if (path == QTET_PATH_SPLIT) {
+        if (!split_eligible(p->view)) { set_error("split path needs a tridiagonal H with dim <= 32"); return QTET_EUNSUPPORTED; }
+        p->path = path;
+        return QTET_OK;
+    }
+    set_error("unknown path");
+    return QTET_EINVAL;
+}
+
+int qtet_get_path(const qtet_problem* p) { return p ? p->path : QTET_EINVAL; }
+
+static int check_call(qtet_problem* p, const void* chis, int64_t B, int site) {
+    if (!p) { set_error("null handle"); return QTET_EINVAL; }
+    if (B < 0) { set_error("negative batch"); return QTET_EINVAL; }
+    if (B > 0 && !chis) { set_error("chis is NULL"); return QTET_EINVAL; }
+    if (site < 0 || site >= p->f) { set_error("target_site out of range"); return QTET_EINVAL; }
+    return QTET_OK;
+}
+
+int qtet_loss_grad(qtet_problem* p, const double* chis_dev, int64_t B, int target_site,
+                   double* loss_dev, double* grad_dev, int32_t* tstar_dev, void* stream) {
+    int rc = check_call(p, chis_dev, B, target_site);
+    if (rc) return rc;
+    if (B == 0) return QTET_OK;
+    if (!loss_dev) { set_error("loss is NULL"); return QTET_EINVAL; }
+    QTET_CUDA(cudaSetDevice(p->device));
+    return loss_grad_dispatch(p, chis_dev, B, target_site, loss_dev, grad_dev, tstar_dev, nullptr, (cudaStream_t)stream);
+}
+
+int qtet_trace(qtet_problem* p, const double* chis_dev, int64_t B, int target_site, double* trace_dev, void* stream) {
+    int rc = check_call(p, chis_dev, B, target_site);
+    if (rc) return rc;
+    if (B == 0) return QTET_OK;
+    if (!trace_dev) { set_error("trace is NULL"); return QTET_EINVAL; }
+    QTET_CUDA(cudaSetDevice(p->device));
+    return loss_grad_dispatch(p, chis_dev, B, target_site, nullptr, nullptr, nullptr, trace_dev, (cudaStream_t)stream);
+}
+
+int qtet_loss_grad_host(qtet_problem* p, const double* chis_host, int64_t B, int target_site,
+                        double* loss_host, double* grad_host, int32_t* tstar_host) {
+    int rc = check_call(p, chis_host, B, target_site);
+    if (rc) return rc;
+    if (B == 0) return QTET_OK;
+    if (!loss_host) { set_error("loss is NULL"); return QTET_EINVAL; }
+    QTET_CUDA(cudaSetDevice(p->device));
+    const size_t f = p->f;
+    const size_t nb_chi = (size_t)B * f * 8, nb_loss = (size_t)B * 8, nb_grad = (size_t)B * f * 8, nb_t = (size_t)B * 4;
+    rc = ensure_scratch(p, nb_chi + nb_loss + nb_grad + nb_t + 64);
+    if (rc) return rc;
+    char* base = (char*)p->scratch;
+    double* dchi = (double*)base;
+    double* dloss = (double*)(base + nb_chi);
+    double* dgrad = (double*)(base + nb_chi + nb_loss);
+    int32_t* dts = (int32_t*)(base + nb_chi + nb_loss + nb_grad);
+    cudaStream_t st = nullptr;
+    QTET_CUDA(cudaMemcpyAsync(dchi, chis_host, nb_chi, cudaMemcpyHostToDevice, st));
+    rc = loss_grad_dispatch(p, dchi, B, target_site, dloss, grad_host ? dgrad : nullptr, tstar_host ? dts : nullptr, nullptr, st);
+    if (rc) return rc;
+    QTET_CUDA(cudaMemcpyAsync(loss_host, dloss, nb_loss, cudaMemcpyDeviceToHost, st));
+    if (grad_host) QTET_CUDA(cudaMemcpyAsync(grad_host, dgrad, nb_grad, cudaMemcpyDeviceToHost, st));
+    if (tstar_host) QTET_CUDA(cudaMemcpyAsync(tstar_host, dts, nb_t, cudaMemcpyDeviceToHost, st));
+    QTET_CUDA(cudaStreamSynchronize(st));
+    return QTET_OK;
+}
+
+int qtet_hamiltonian_host(qtet_problem* p, const double* chis_host, double* H_host) {
+    if (!p || !chis_host || !H_host) { set_error("null argument"); return QTET_EINVAL; }
+    QTET_CUDA(cudaSetDevice(p->device));
+    const size_t nH = (size_t)p->d * p->d * 8, nchi = (size_t)p->f * 8;
+    int rc = ensure_scratch(p, nH + nchi + 64);
+    if (rc) return rc;
+    double* dchi = (double*)p->scratch;
+    double* dH = (double*)((char*)p->scratch + ((nchi + 63) / 64) * 64);
+    QTET_CUDA(cudaMemcpy(dchi, chis_host, nchi, cudaMemcpyHostToDevice));
+    rc = launch_build_h(p->view, dchi, dH, nullptr);
+    if (rc) return rc;
+    QTET_CUDA(cudaMemcpy(H_host, dH, nH, cudaMemcpyDeviceToHost));
+    return QTET_OK;
+}
+
+int qtet_argmin(const double* values_dev, int64_t B, double* min_dev, int64_t* idx_dev, void* stream) {
+    if (B <= 0 || !values_dev || !min_dev || !idx_dev) { set_error("bad argument"); return QTET_EINVAL; }
+    return launch_argmin(values_dev, B, min_dev, idx_dev, (cudaStream_t)stream);
+}
+
+int64_t qtet_launch_count(void) { return g_launches.load(); }
+const char* qtet_last_error(void) { return g_last_error.c_str(); }
+const char* qtet_version(void) { return "qtet-b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

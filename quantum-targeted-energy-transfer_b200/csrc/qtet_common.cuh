@@ -1,0 +1,110 @@
+// Shared declarations of libqtet_b200 (host handle, device views, small device helpers).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/qtet.h"
+
+namespace qtet {
+
+// Device-side, chi-independent description of one problem (all pointers on the device).
+struct ProblemView {
+    int N, f, d, T;
+    int tridiag;          // 1: H is tridiagonal in the reference's basis order (dimer)
+    double max_t;
+    const double* lin;    // [d]     sum_k omega_k n_k(m)                 HamiltonianLoss.py:132-133
+    const double* quad;   // [d, f]  n_k(m)^2 / 2 = dH_mm/dchi_k          HamiltonianLoss.py:134
+    const double* occ;    // [d, f]  n_k(m)                               HamiltonianLoss.py:62-110
+    const double* offd;   // tridiag: [d-1] H[m+1,m]; dense: [d, d] hopping part   :136-163
+    const double* tgrid;  // [T]     linspace(0, max_t, T)                HamiltonianLoss.py:221
+    const double* omegas; // [f]
+};
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+void count_launch(int n = 1);
+
+#define QTET_CUDA(call)                                             \
+    do {                                                            \
+        cudaError_t _e = (call);                                    \
+        if (_e != cudaSuccess) return ::qtet::cuda_fail(_e, #call); \
+    } while (0)
+
+// ---- launchers implemented in the kernel translation units -------------------------------
+int launch_generic(const ProblemView& pv, const double* chis, int64_t B, int site, double* loss,
+                   double* grad, int32_t* tstar, double* trace, cudaStream_t st);
+size_t generic_smem_bytes(int d, int nthreads);
+int generic_threads(int d);
+int launch_build_h(const ProblemView& pv, const double* chis, double* H, cudaStream_t st);
+
+struct SplitWorkspace;   // rotation streams etc. (qtet_split.cu)
+bool split_eligible(const ProblemView& pv);
+int launch_split(const ProblemView& pv, SplitWorkspace** ws, const double* chis, int64_t B, int site,
+                 double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st);
+void split_workspace_free(SplitWorkspace* ws);
+
+int launch_argmin(const double* v, int64_t B, double* min_out, int64_t* idx_out, cudaStream_t st);
+
+struct AdamState;        // per-guess optimiser state on the device (qtet_adam.cu)
+
+}  // namespace qtet
+
+struct qtet_problem {
+    int N, f, d, T, device;
+    double coupling, max_t;
+    bool tridiag;
+    int path;                               // QTET_PATH_*
+    std::vector<double> omegas, states, tgrid;
+    double* dev_blob = nullptr;             // one allocation holding every constant array
+    qtet::ProblemView view{};
+    qtet::SplitWorkspace* split_ws = nullptr;
+    // scratch for *_host convenience calls and the optimiser
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+
+namespace qtet {
+int ensure_scratch(qtet_problem* p, size_t bytes);
+int loss_grad_dispatch(qtet_problem* p, const double* chis, int64_t B, int site, double* loss,
+                       double* grad, int32_t* tstar, double* trace, cudaStream_t st);
+}
+
+// ---- device helpers ---------------------------------------------------------------------
+#ifdef __CUDACC__
+namespace qtet {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// (exp(-i x) - 1) / x, accurate for |x| <= 1e-2 (series to x^7)
+__device__ __forceinline__ void expm1_over_x(double x, double& re, double& im) {
+    const double x2 = x * x;
+    re = x * (-0.5 + x2 * (1.0 / 24.0 + x2 * (-1.0 / 720.0 + x2 * (1.0 / 40320.0))));
+    im = -1.0 + x2 * (1.0 / 6.0 + x2 * (-1.0 / 120.0 + x2 * (1.0 / 5040.0)));
+}
+
+// Daleckii-Krein divided difference of exp(-i e t) between eigenvalues (ei, fi) and (ej, fj):
+// (f_i - f_j)/(e_i - e_j), degeneracy-safe; fi/fj are the unit phases exp(-i e t).
+__device__ __forceinline__ void dk_phi(double ei, double fir, double fii, double ej, double fjr,
+                                       double fji, double t, double& pr, double& pi) {
+    const double dl = ei - ej;
+    const double x = dl * t;
+    if (fabs(x) < 1e-2) {
+        double gr, gi;
+        expm1_over_x(x, gr, gi);
+        pr = t * (fjr * gr - fji * gi);
+        pi = t * (fjr * gi + fji * gr);
+    } else {
+        const double inv = 1.0 / dl;
+        pr = (fir - fjr) * inv;
+        pi = (fii - fji) * inv;
+    }
+}
+
+}  // namespace qtet
+#endif

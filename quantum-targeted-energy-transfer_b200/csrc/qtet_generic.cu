@@ -1,0 +1,394 @@
+// Fused generic kernel: one CTA per parameter point, any Fock dimension that fits shared memory.
+//
+//   H build (HamiltonianLoss.py:124-176) -> [Householder tridiagonalisation if H is not tridiagonal]
+//   -> implicit-shift QL with accumulated eigenvectors (replaces tf.linalg.eigh, :182)
+//   -> psi_j(t) = sum_i V_ji c_i exp(-i e_i t), <n(t)> = sum_j n_site(j) |psi_j|^2   (:204-215)
+//   -> loss = N - max_t / min_t (:227-231) -> analytic gradient (replaces Optimizer.py:85-91).
+//
+// Everything lives in shared memory: V [d x ldv] (eigenvectors) and M [d x ldv] (the dense matrix
+// during tridiagonalisation, later the Daleckii-Krein kernel K).  Every warp keeps a private copy of
+// the tridiagonal (diag/off) and runs the scalar QL recurrence redundantly, so the QL phase needs no
+// block-level barrier: each thread applies the rotations to its own rows of V.
+//
+// This kernel is the general/robust path (trimer, large dimers) and the on-GPU cross-check of the
+// fast split path in qtet_split.cu.
+#include "qtet_common.cuh"
+
+namespace qtet {
+
+namespace {
+
+constexpr double kEps = 1.1102230246251565e-16;   // 2^-53
+constexpr int kMaxQlIter = 60;
+
+struct GenericArgs {
+    ProblemView pv;
+    const double* chis;
+    long long B;
+    int site;
+    int acceptor;
+    int ldv;
+    double* loss;
+    double* grad;
+    int* tstar;
+    double* trace;
+};
+
+__device__ __forceinline__ double block_sum(double v, double* red, int tid, int nwarps) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < nwarps; ++w) s += red[w];
+    return s;
+}
+
+__global__ void generic_kernel(GenericArgs a) {
+    extern __shared__ double smem[];
+    const ProblemView& pv = a.pv;
+    const int d = pv.d, f = pv.f, T = pv.T, ld = a.ldv;
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
+
+    double* V = smem;                       // [d][ld]
+    double* M = V + (size_t)d * ld;         // [d][ld]
+    double* wdiag = M + (size_t)d * ld;     // [nwarps][d]
+    double* woff = wdiag + nwarps * d;      // [nwarps][d]
+    double* cvec = woff + nwarps * d;       // [d]   c_i = V[0][i]
+    double* zr = cvec + d;                  // [d]
+    double* zi = zr + d;
+    double* fr = zi + d;                    // [d]   exp(-i e_i t*)
+    double* fi = fr + d;
+    double* ar = fi + d;                    // [d]   a = V^T (w conj psi)
+    double* ai = ar + d;
+    double* wr = ai + d;                    // [d]   w_j conj(psi_j) ; also Householder v
+    double* wi = wr + d;                    // [d]   also Householder w
+    double* tr = wi + d;                    // [T]
+    double* red = tr + T;                   // [32]
+    int* ired = (int*)(red + 32);           // [4]
+
+    double* mydiag = wdiag + warp * d;
+    double* myoff = woff + warp * d;
+
+    for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
+        const double* chi = a.chis + b * f;
+        __syncthreads();
+        // ---------------------------------------------------------------- H build
+        // V <- identity
+        for (int idx = tid; idx < d * d; idx += nth) {
+            const int r = idx / d, c = idx - r * d;
+            V[r * ld + c] = (r == c) ? 1.0 : 0.0;
+        }
+        if (pv.tridiag) {
+            for (int m = lane; m < d; m += 32) {
+                double acc = 0.0;
+                for (int k = 0; k < f; ++k)
+                    acc = acc + (pv.omegas[k] * pv.occ[m * f + k] + (0.5 * chi[k]) * (pv.occ[m * f + k] * pv.occ[m * f + k]));
+                mydiag[m] = acc;
+                myoff[m] = (m < d - 1) ? pv.offd[m] : 0.0;
+            }
+            __syncwarp();
+        } else {
+            // dense symmetric H into M, then Householder reduction to tridiagonal form with the
+            // orthogonal factor accumulated (forward) into V.  Row/col 0 of Q stay e_0.
+            for (int idx = tid; idx < d * d; idx += nth) {
+                const int r = idx / d, c = idx - r * d;
+                double h = pv.offd[idx];
+                if (r == c) {
+                    double acc = 0.0;
+                    for (int k = 0; k < f; ++k)
+                        acc = acc + (pv.omegas[k] * pv.occ[r * f + k] + (0.5 * chi[k]) * (pv.occ[r * f + k] * pv.occ[r * f + k]));
+                    h = acc;
+                }
+                M[r * ld + c] = h;
+            }
+            __syncthreads();
+            for (int k = 0; k < d - 2; ++k) {
+                const int n = d - k - 1;            // length of the column below the diagonal
+                const int o = k + 1;
+                double part = 0.0;
+                for (int i = 1 + tid; i < n; i += nth) { const double x = M[(o + i) * ld + k]; part += x * x; }
+                const double sigma = block_sum(part, red, tid, nwarps);
+                const double x0 = M[o * ld + k];
+                if (sigma == 0.0) {                 // nothing to annihilate
+                    for (int w = tid; w < nwarps; w += nth) { wdiag[w * d + k] = M[k * ld + k]; woff[w * d + k] = x0; }
+                    __syncthreads();
+                    continue;
+                }
+                const double mu = sqrt(x0 * x0 + sigma);
+                const double alpha = (x0 >= 0.0) ? -mu : mu;
+                const double v0 = x0 - alpha;
+                const double beta = 2.0 / (v0 * v0 + sigma);
+                for (int i = tid; i < n; i += nth) wr[i] = (i == 0) ? v0 : M[(o + i) * ld + k];
+                __syncthreads();
+                // p = beta * A22 v
+                double vp = 0.0;
+                for (int i = tid; i < n; i += nth) {
+                    const double* row = M + (size_t)(o + i) * ld + o;
+                    double acc = 0.0;
+                    for (int j = 0; j < n; ++j) acc = fma(row[j], wr[j], acc);
+                    acc *= beta;
+                    wi[i] = acc;
+                    vp = fma(wr[i], acc, vp);
+                }
+                const double kk = 0.5 * beta * block_sum(vp, red, tid, nwarps);
+                for (int i = tid; i < n; i += nth) wi[i] = wi[i] - kk * wr[i];
+                __syncthreads();
+                // A22 -= v w^T + w v^T ;  Q[:, o:] -= beta (Q[:, o:] v) v^T
+                for (int i = tid; i < n; i += nth) {
+                    double* row = M + (size_t)(o + i) * ld + o;
+                    const double vi = wr[i], wi_ = wi[i];
+                    for (int j = 0; j < n; ++j) row[j] -= vi * wi[j] + wi_ * wr[j];
+                }
+                for (int r = tid; r < d; r += nth) {
+                    double* row = V + (size_t)r * ld + o;
+                    double u = 0.0;
+                    for (int j = 0; j < n; ++j) u = fma(row[j], wr[j], u);
+                    u *= beta;
+                    for (int j = 0; j < n; ++j) row[j] = fma(-u, wr[j], row[j]);
+                }
+                for (int w = tid; w < nwarps; w += nth) { wdiag[w * d + k] = M[k * ld + k]; woff[w * d + k] = alpha; }
+                __syncthreads();
+            }
+            for (int w = tid; w < nwarps; w += nth) {
+                if (d >= 2) {
+                    wdiag[w * d + d - 2] = M[(d - 2) * ld + d - 2];
+                    woff[w * d + d - 2] = M[(d - 1) * ld + d - 2];
+                }
+                wdiag[w * d + d - 1] = M[(d - 1) * ld + d - 1];
+                woff[w * d + d - 1] = 0.0;
+            }
+            __syncthreads();
+        }
+
+        // ---------------------------------------------------------------- implicit QL
+        // Scalar recurrences are computed redundantly by every lane on the warp-private copy;
+        // each thread rotates its own rows of V.  (Algorithm: implicit-shift QL with Wilkinson shift.)
+        {
+            double* dg = mydiag;
+            double* of = myoff;
+            for (int l = 0; l < d; ++l) {
+                int iter = 0;
+                while (true) {
+                    int m = l;
+                    for (; m < d - 1; ++m) {
+                        const double dd = fabs(dg[m]) + fabs(dg[m + 1]);
+                        if (fabs(of[m]) <= kEps * dd) break;
+                    }
+                    if (m == l) break;
+                    if (++iter > kMaxQlIter) break;
+                    double g = (dg[l + 1] - dg[l]) / (2.0 * of[l]);
+                    double r = sqrt(g * g + 1.0);
+                    g = dg[m] - dg[l] + of[l] / (g + copysign(r, g));
+                    double s = 1.0, c = 1.0, p = 0.0;
+                    int i = m - 1;
+                    bool underflow = false;
+                    __syncwarp();
+                    for (; i >= l; --i) {
+                        const double fo = s * of[i];
+                        const double bo = c * of[i];
+                        r = sqrt(fo * fo + g * g);
+                        __syncwarp();
+                        if (lane == 0) of[i + 1] = r;
+                        if (r == 0.0) {
+                            if (lane == 0) { dg[i + 1] -= p; of[m] = 0.0; }
+                            underflow = true;
+                            break;
+                        }
+                        const double rinv = 1.0 / r;
+                        s = fo * rinv;
+                        c = g * rinv;
+                        g = dg[i + 1] - p;
+                        r = (dg[i] - g) * s + 2.0 * c * bo;
+                        p = s * r;
+                        __syncwarp();
+                        if (lane == 0) dg[i + 1] = g + p;
+                        g = c * r - bo;
+                        for (int row = tid; row < d; row += nth) {
+                            double* vr = V + (size_t)row * ld;
+                            const double y = vr[i + 1], x = vr[i];
+                            vr[i + 1] = fma(s, x, c * y);
+                            vr[i] = fma(c, x, -(s * y));
+                        }
+                    }
+                    __syncwarp();
+                    if (underflow) continue;
+                    if (lane == 0) { dg[l] -= p; of[l] = g; of[m] = 0.0; }
+                    __syncwarp();
+                }
+            }
+        }
+        __syncthreads();
+        const double* ev = wdiag;           // warp 0's copy (all identical)
+        for (int i = tid; i < d; i += nth) cvec[i] = V[i];    // c = V[0,:]
+        __syncthreads();
+
+        // ---------------------------------------------------------------- evolution + loss
+        for (int k = 0; k < T; ++k) {
+            const double t = pv.tgrid[k];
+            for (int i = tid; i < d; i += nth) {
+                double sn, cs;
+                sincos(ev[i] * t, &sn, &cs);
+                zr[i] = cvec[i] * cs;
+                zi[i] = -cvec[i] * sn;
+            }
+            __syncthreads();
+            double part = 0.0;
+            for (int j = tid; j < d; j += nth) {
+                const double* row = V + (size_t)j * ld;
+                double pr = 0.0, pi = 0.0;
+                for (int i = 0; i < d; ++i) { pr = fma(row[i], zr[i], pr); pi = fma(row[i], zi[i], pi); }
+                part = fma(pv.occ[j * f + a.site], pr * pr + pi * pi, part);
+            }
+            const double nk = block_sum(part, red, tid, nwarps);
+            if (tid == 0) tr[k] = nk;
+        }
+        __syncthreads();
+        if (a.trace != nullptr)
+            for (int k = tid; k < T; k += nth) a.trace[b * T + k] = tr[k];
+        if (tid == 0) {
+            int best = 0;
+            double bv = tr[0];
+            for (int k = 1; k < T; ++k) {
+                const bool better = a.acceptor ? (tr[k] > bv) : (tr[k] < bv);
+                if (better) { bv = tr[k]; best = k; }
+            }
+            ired[0] = best;
+            if (a.loss) a.loss[b] = a.acceptor ? ((double)pv.N - bv) : bv;
+            if (a.tstar) a.tstar[b] = best;
+        }
+        __syncthreads();
+        if (a.grad == nullptr) continue;
+
+        // ---------------------------------------------------------------- gradient
+        const int ks = ired[0];
+        const double ts = pv.tgrid[ks];
+        for (int i = tid; i < d; i += nth) {
+            double sn, cs;
+            sincos(ev[i] * ts, &sn, &cs);
+            fr[i] = cs; fi[i] = -sn;
+            zr[i] = cvec[i] * cs; zi[i] = -cvec[i] * sn;
+        }
+        __syncthreads();
+        for (int j = tid; j < d; j += nth) {
+            const double* row = V + (size_t)j * ld;
+            double pr = 0.0, pi = 0.0;
+            for (int i = 0; i < d; ++i) { pr = fma(row[i], zr[i], pr); pi = fma(row[i], zi[i], pi); }
+            const double w = pv.occ[j * f + a.site];
+            wr[j] = w * pr;            // w conj(psi)
+            wi[j] = -w * pi;
+        }
+        __syncthreads();
+        for (int i = tid; i < d; i += nth) {
+            double sr = 0.0, si = 0.0;
+            for (int j = 0; j < d; ++j) { const double v = V[(size_t)j * ld + i]; sr = fma(v, wr[j], sr); si = fma(v, wi[j], si); }
+            ar[i] = sr; ai[i] = si;
+        }
+        __syncthreads();
+        // K_ij = Re(a_i c_j Phi_ij)
+        for (int idx = tid; idx < d * d; idx += nth) {
+            const int i = idx / d, j = idx - i * d;
+            double pr, pi;
+            if (i == j) { pr = ts * fi[i]; pi = -ts * fr[i]; }
+            else dk_phi(ev[i], fr[i], fi[i], ev[j], fr[j], fi[j], ts, pr, pi);
+            M[i * ld + j] = cvec[j] * (ar[i] * pr - ai[i] * pi);
+        }
+        __syncthreads();
+        double gacc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) gacc[k] = 0.0;
+        for (int m = tid; m < d; m += nth) {
+            const double* row = V + (size_t)m * ld;
+            double G = 0.0;
+            for (int i = 0; i < d; ++i) {
+                const double* kr = M + (size_t)i * ld;
+                double acc = 0.0;
+                for (int j = 0; j < d; ++j) acc = fma(kr[j], row[j], acc);
+                G = fma(row[i], acc, G);
+            }
+            G *= 2.0;
+            for (int k = 0; k < f && k < 8; ++k) gacc[k] = fma(pv.quad[m * f + k], G, gacc[k]);
+        }
+        for (int k = 0; k < f && k < 8; ++k) {
+            const double s = block_sum(gacc[k], red, tid, nwarps);
+            if (tid == 0) a.grad[b * f + k] = a.acceptor ? -s : s;
+        }
+    }
+}
+
+__global__ void build_h_kernel(ProblemView pv, const double* chi, double* H) {
+    const int d = pv.d, f = pv.f;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < d * d; idx += gridDim.x * blockDim.x) {
+        const int r = idx / d, c = idx - r * d;
+        double h = 0.0;
+        if (r == c) {
+            double acc = 0.0;
+            for (int k = 0; k < f; ++k)
+                acc = acc + (pv.omegas[k] * pv.occ[r * f + k] + (0.5 * chi[k]) * (pv.occ[r * f + k] * pv.occ[r * f + k]));
+            h = acc;
+        } else if (pv.tridiag) {
+            if (r == c + 1) h = pv.offd[c];
+            else if (c == r + 1) h = pv.offd[r];
+        } else {
+            h = pv.offd[idx];
+        }
+        H[idx] = h;
+    }
+}
+
+}  // namespace
+
+int generic_threads(int d) {
+    int t = ((d + 31) / 32) * 32;
+    if (t < 32) t = 32;
+    if (t > 128) t = 128;
+    return t;
+}
+
+static int generic_ld(int d) { return d | 1; }
+
+size_t generic_smem_bytes(int d, int nthreads) {
+    const int nw = nthreads / 32;
+    const size_t ld = generic_ld(d);
+    size_t n = 2 * (size_t)d * ld + 2 * (size_t)nw * d + 9 * (size_t)d + 64 /*tr, up to T=64*/ + 32 + 2;
+    return n * sizeof(double);
+}
+
+int launch_generic(const ProblemView& pv, const double* chis, int64_t B, int site, double* loss,
+                   double* grad, int32_t* tstar, double* trace, cudaStream_t st) {
+    if (B <= 0) return QTET_OK;
+    if (pv.f > 8) { set_error("generic kernel supports at most 8 sites"); return QTET_EUNSUPPORTED; }
+    const int nth = generic_threads(pv.d);
+    size_t smem = generic_smem_bytes(pv.d, nth) + (pv.T > 64 ? (pv.T - 64) * sizeof(double) : 0);
+    int dev = 0, max_optin = 0, sms = 0;
+    QTET_CUDA(cudaGetDevice(&dev));
+    QTET_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    QTET_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (smem > (size_t)max_optin) {
+        set_error("Fock dimension " + std::to_string(pv.d) + " needs " + std::to_string(smem) +
+                  " B of shared memory per CTA; device limit is " + std::to_string(max_optin));
+        return QTET_EUNSUPPORTED;
+    }
+    QTET_CUDA(cudaFuncSetAttribute(generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    QTET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, generic_kernel, nth, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)sms * per_sm;     // persistent: a whole number of waves of the 148 SMs
+    if (grid > B) grid = B;
+    GenericArgs a;
+    a.pv = pv; a.chis = chis; a.B = B; a.site = site; a.acceptor = (site == pv.f - 1) ? 1 : 0;
+    a.ldv = generic_ld(pv.d); a.loss = loss; a.grad = grad; a.tstar = tstar; a.trace = trace;
+    generic_kernel<<<(unsigned)grid, nth, smem, st>>>(a);
+    count_launch();
+    QTET_CUDA(cudaGetLastError());
+    return QTET_OK;
+}
+
+int launch_build_h(const ProblemView& pv, const double* chis, double* H, cudaStream_t st) {
+    build_h_kernel<<<8, 256, 0, st>>>(pv, chis, H);
+    count_launch();
+    QTET_CUDA(cudaGetLastError());
+    return QTET_OK;
+}
+
+}  // namespace qtet

@@ -1,0 +1,53 @@
+"""`Loss` -- the reference's loss object (/root/reference/src/tet/HamiltonianLoss.py:12-233) on the
+B200 kernels.  Same constructor and call signature; returns 0-d float64 tensors (`.numpy()` works as on
+an eager tf.Tensor).  Extra, batched entry points (`batch`, `batch_trace`) expose what the kernels do
+natively: many parameter points per call."""
+import numpy as np
+
+from . import _native
+
+DTYPE = 'float64'
+
+
+def _as_float(x):
+    if hasattr(x, 'numpy'):
+        x = x.numpy()
+    return float(np.asarray(x))
+
+
+class Loss:
+    """Loss(const) with const as in tet.constants.system_constants (HamiltonianLoss.py:20-47)."""
+
+    def __init__(self, const, device=None):
+        self.const = const
+        self.max_N_np = const['max_N']
+        self.NpointsT = const['timesteps']
+        self.sites = const['sites']
+        self.chis = const['chis']
+        self.targetState = const['sites'] - 1          # HamiltonianLoss.py:36
+        self.problem = _native.Problem.from_const(const, device)
+        self.dim = self.problem.dim
+        self.states = self.problem.states()            # HamiltonianLoss.py:43, 62-110
+
+    def __call__(self, chis, site=0, single_value=True):
+        """HamiltonianLoss.py:49-60.  `site`: int, or a string ending in the site digit ('x1')."""
+        import torch
+        self.chis = chis
+        self.targetState = self.problem._site(site)
+        x = np.array([[_as_float(c) for c in chis]], dtype=np.float64)
+        if single_value:
+            loss, _, _ = self.problem.loss_grad(x, self.targetState, need_grad=False, need_tstar=False)
+            return loss[0].cpu()
+        return self.problem.trace(x, self.targetState)[0].cpu()
+
+    # ---- batched API (what replaces the process pool) -------------------------------------
+    def batch(self, chis, site=None):
+        """chis [B,f] -> (loss[B], grad[B,f], t_star[B]) torch CUDA tensors."""
+        return self.problem.loss_grad(chis, self.sites - 1 if site is None else site)
+
+    def batch_trace(self, chis, site=None):
+        return self.problem.trace(chis, self.sites - 1 if site is None else site)
+
+    def createHamiltonian(self):
+        """HamiltonianLoss.py:168-176 for the current self.chis (device-built, returned as numpy)."""
+        return self.problem.hamiltonian([_as_float(c) for c in self.chis])

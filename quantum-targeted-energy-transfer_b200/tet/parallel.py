@@ -1,0 +1,79 @@
+"""Data parallelism over initial guesses / parameter points: one process per GPU, contiguous shards,
+no collective during evaluation, ONE tiny collective at the end (global arg-min).
+
+Replaces multiprocessing.Pool + np.argmin of /root/reference/src/tet/solver_mp.py:157-184.
+Works with torch.distributed backend 'nccl' (device tensors over NVLink/NVSwitch) and 'gloo' (CPU tests).
+"""
+import numpy as np
+
+
+def world():
+    """(rank, world_size) -- (0, 1) when torch.distributed is not initialised."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return 0, 1
+
+
+def shard_bounds(n: int, rank: int, world_size: int):
+    """Contiguous, balanced shard [lo, hi) of n items for `rank` (first n % world shards get one more)."""
+    base, rem = divmod(n, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def global_argmin(local_rows: np.ndarray, lo: int, loss_col: int):
+    """Each rank holds rows [lo, lo+n) of the [G, f+1] result array.  Returns (global_index, row) of the
+    smallest loss over all ranks; ties -> smallest global index (what np.argmin on the gathered array gives,
+    solver_mp.py:183-184).  One all_gather of a (f+3)-double record per rank."""
+    import torch
+    import torch.distributed as dist
+    rank, ws = world()
+    width = local_rows.shape[1] if local_rows.ndim == 2 else loss_col + 1
+    rec = np.full(width + 2, np.inf)
+    if local_rows.shape[0] > 0:
+        j = int(np.argmin(local_rows[:, loss_col]))
+        rec[0] = local_rows[j, loss_col]
+        rec[1] = float(lo + j)
+        rec[2:] = local_rows[j]
+    else:
+        rec[1] = float(2 ** 52)
+        rec[2:] = 0.0
+    if ws == 1:
+        return int(rec[1]), rec[2:].copy()
+    backend = dist.get_backend()
+    dev = torch.device('cuda', torch.cuda.current_device()) if backend == 'nccl' else torch.device('cpu')
+    mine = torch.from_numpy(rec).to(dev)
+    gathered = [torch.empty_like(mine) for _ in range(ws)]
+    dist.all_gather(gathered, mine)
+    table = torch.stack(gathered).cpu().numpy()
+    order = np.lexsort((table[:, 1], table[:, 0]))          # by loss, then by global index
+    best = table[order[0]]
+    return int(best[1]), best[2:].copy()
+
+
+def gather_rows(local_rows: np.ndarray, n_total: int, lo: int):
+    """All-gather variable-length shards of rows into the full [n_total, width] array (used only when the
+    caller asks for every guess' result, e.g. write_data; the solver itself needs just the arg-min)."""
+    import torch
+    import torch.distributed as dist
+    rank, ws = world()
+    if ws == 1:
+        return local_rows
+    width = local_rows.shape[1]
+    backend = dist.get_backend()
+    dev = torch.device('cuda', torch.cuda.current_device()) if backend == 'nccl' else torch.device('cpu')
+    pad = -(-n_total // ws)
+    buf = np.zeros((pad, width))
+    buf[:local_rows.shape[0]] = local_rows
+    mine = torch.from_numpy(buf).to(dev)
+    gathered = [torch.empty_like(mine) for _ in range(ws)]
+    dist.all_gather(gathered, mine)
+    out = np.zeros((n_total, width))
+    for r in range(ws):
+        a, b = shard_bounds(n_total, r, ws)
+        out[a:b] = gathered[r].cpu().numpy()[:b - a]
+    return out

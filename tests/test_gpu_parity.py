@@ -1,0 +1,185 @@
+"""GPU parity tests (run with `-m gpu` on a B200): the CUDA path, called through the C ABI
+(tet._native -> libqtet_b200.so), against the CPU oracle on the same seeded inputs, against the golden
+vectors produced by the unmodified reference, and -- at BASELINE sizes -- through size-independent
+properties (boson-number conservation, initial condition, bounds).
+
+Tolerances (FP64 path vs the FP64/complex128 oracle; the reference itself evolves in complex64 and is
+only good to ~1e-5, see tests/test_oracle.py):
+    loss   : |dL|  <= LOSS_ATOL * max(1, N)      absolute     (phase errors scale with eps*||H||*max_t)
+    grad   : |dg|  <= GRAD_RTOL * max(1, max|g|) per point
+    t_star : identical, except where the two best samples are closer than the loss tolerance
+"""
+import numpy as np
+import pytest
+
+from conftest import make_const
+
+pytestmark = pytest.mark.gpu
+
+LOSS_ATOL = 1e-10
+GRAD_RTOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def native():
+    from tet import _native
+    return _native
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import qtet_oracle
+    return qtet_oracle
+
+
+def _compare(native, O, const, X, site, path=None, loss_atol=None, grad_rtol=None):
+    prob = native.Problem.from_const(const)
+    if path is not None:
+        prob.set_path(path)
+    loss, grad, ts = prob.loss_grad(X, site)
+    loss, grad, ts = loss.cpu().numpy(), grad.cpu().numpy(), ts.cpu().numpy()
+    Lr, gr, kr = O.loss_grad_batch(const, X, site)
+    N = const["max_N"]
+    la = (loss_atol or LOSS_ATOL) * max(1, N)
+    assert np.isfinite(loss).all() and np.isfinite(grad).all()
+    assert np.abs(loss - Lr).max() <= la, np.abs(loss - Lr).max()
+    same_t = ts == kr
+    if not same_t.all():
+        # a different arg-max sample is acceptable only on a numerical tie of the two samples
+        tr = O.trace(const, X[~same_t], site)
+        idx = np.arange(tr.shape[0])
+        assert np.abs(tr[idx, ts[~same_t]] - tr[idx, kr[~same_t]]).max() <= la
+    gscale = np.maximum(1.0, np.abs(gr).max(axis=1, keepdims=True))
+    err = (np.abs(grad - gr) / gscale)[same_t]
+    assert err.max() <= (grad_rtol or GRAD_RTOL), err.max()
+    prob.close()
+    return np.abs(loss - Lr).max(), err.max()
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 4, 7, 20, 31])
+@pytest.mark.parametrize("site", [1, 0])
+def test_dimer_loss_grad_vs_oracle(native, O, N, site):
+    rng = np.random.default_rng(100 + N)
+    X = rng.uniform(-10, 10, (257, 2))
+    _compare(native, O, make_const(N), X, site)
+
+
+@pytest.mark.parametrize("N", [3, 20, 31])
+def test_dimer_generic_path_vs_oracle(native, O, N):
+    rng = np.random.default_rng(7 + N)
+    X = rng.uniform(-10, 10, (130, 2))
+    _compare(native, O, make_const(N), X, 1, path=native.QTET_PATH_GENERIC)
+
+
+def test_dimer_large_fock_space(native, O):
+    # BASELINE config 3 shape (dimer N=100, d=101); phases reach |e t| ~ 1e6 so the tolerance is the
+    # eps*||H||*max_t scale of SURVEY.md §7 ("hard parts")
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-10, 10, (48, 2))
+    _compare(native, O, make_const(100), X, 1, loss_atol=2e-9, grad_rtol=2e-6)
+
+
+@pytest.mark.parametrize("N,omegas", [(2, (-3, 3, 3)), (4, (-3, 3, 3)), (10, (-3, 3, 3)), (5, (-3, 1, 3)), (3, (-3, 0, 1, 3))])
+def test_chain_loss_grad_vs_oracle(native, O, N, omegas):
+    rng = np.random.default_rng(N)
+    f = len(omegas)
+    X = rng.uniform(-10, 10, (96, f))
+    for site in (f - 1, 0, 1):
+        _compare(native, O, make_const(N, omegas), X, site, loss_atol=2e-10, grad_rtol=5e-8)
+
+
+def test_golden_reference_vectors(native, golden):
+    # values produced by the reference's own HamiltonianLoss.py (c128 stand-in arithmetic)
+    for r in golden["loss"]:
+        prob = native.Problem.from_const(r["const"])
+        loss, _, _ = prob.loss_grad(np.array([r["chis"]]), r["site"])
+        tr = prob.trace(np.array([r["chis"]]), r["site"])[0].cpu().numpy()
+        assert abs(float(loss[0]) - r["loss_c128"]) < 1e-10
+        assert np.abs(tr - np.array(r["trace_c128"])).max() < 1e-10
+        # and within float32 noise of the reference's real (complex64) arithmetic
+        assert abs(float(loss[0]) - r["loss_c64"]) < 1e-4
+        prob.close()
+
+
+def test_basis_and_hamiltonian(native, O, golden):
+    for b in golden["basis"]:
+        prob = native.Problem(b["max_N"], b["sites"], [-3, 3] + [3] * (b["sites"] - 2), 1.0, 25, 30)
+        assert prob.dim == b["dim"]
+        assert prob.states().astype(int).tolist() == b["states"]
+        prob.close()
+    for h in golden["hamiltonian"]:
+        prob = native.Problem.from_const(h["const"])
+        H = prob.hamiltonian(h["chis"])
+        Href = np.array([float.fromhex(x) for x in h["H_hex"]]).reshape(H.shape)
+        assert np.abs(H - Href).max() <= 4e-16 * max(1.0, np.abs(Href).max())      # fma contraction only
+        prob.close()
+
+
+def test_degenerate_and_resonant_points(native, O):
+    # exact TET resonance (degenerate diagonal), chi = 0, symmetric points, huge nonlinearity
+    c = make_const(20)
+    X = np.array([[0.3, -0.3], [0.0, 0.0], [10.0, 10.0], [-10.0, -10.0], [10.0, -10.0], [1e-9, -1e-9],
+                  [6.0 / 20, -6.0 / 20], [0.6, 0.0], [0.0, -0.6], [5.0, 5.0]])
+    _compare(native, O, c, X, 1)
+    _compare(native, O, c, X, 0)
+    c3 = make_const(4, (-3, 3, 3))
+    X3 = np.array([[0.0, 0.0, 0.0], [1.5, 0.0, -1.5], [2.0, 2.0, 2.0], [10.0, -10.0, 10.0]])
+    _compare(native, O, c3, X3, 2, loss_atol=2e-10, grad_rtol=5e-8)
+
+
+def test_trace_and_conservation_full_size(native):
+    # BASELINE config 2 size sample: sum over sites of <n_k(t)> = N for every t, <n_0(0)> = N, bounds
+    c = make_const(20)
+    ax = np.linspace(-10, 10, 1024)
+    rng = np.random.default_rng(5)
+    X = np.stack([ax[rng.integers(0, 1024, 20000)], ax[rng.integers(0, 1024, 20000)]], axis=1)
+    prob = native.Problem.from_const(c)
+    t0 = prob.trace(X, 0).cpu().numpy()
+    t1 = prob.trace(X, 1).cpu().numpy()
+    assert np.abs(t0 + t1 - 20).max() < 1e-9
+    assert np.abs(t0[:, 0] - 20).max() < 1e-11 and np.abs(t1[:, 0]).max() < 1e-11
+    loss, grad, ts = prob.loss_grad(X, 1)
+    loss = loss.cpu().numpy()
+    assert (loss > -1e-9).all() and (loss < 20 + 1e-9).all()
+    assert np.abs((20 - t1.max(axis=1)) - loss).max() < 1e-12
+    assert (t1.argmax(axis=1) == ts.cpu().numpy()).all()
+    prob.close()
+
+
+def test_host_entry_point_and_edge_batches(native, O):
+    c = make_const(5)
+    prob = native.Problem.from_const(c)
+    rng = np.random.default_rng(2)
+    for B in (1, 2, 31, 33, 1000):
+        X = rng.uniform(-4, 4, (B, 2))
+        L, g, k = prob.loss_grad_host(X, 1)
+        Lr, gr, kr = O.loss_grad_batch(c, X, 1)
+        assert np.abs(L - Lr).max() < 1e-10 and np.abs(g - gr).max() < 1e-8 and (k == kr).all()
+    # empty batch is a no-op
+    L, g, k = prob.loss_grad_host(np.zeros((0, 2)), 1)
+    assert L.shape == (0,)
+    with pytest.raises(ValueError):
+        prob.loss_grad(np.zeros((3, 3)))
+    with pytest.raises(ValueError):
+        prob.loss_grad(np.zeros((3, 2)), site=2)
+    with pytest.raises(ValueError):
+        prob.loss_grad(np.zeros((3, 2)), site=1.0)
+    assert float(prob.loss_grad(np.array([[1.0, -1.0]]), "x1")[0][0]) == float(prob.loss_grad(np.array([[1.0, -1.0]]), 1)[0][0])
+    prob.close()
+
+
+def test_split_and_generic_paths_agree(native):
+    c = make_const(20)
+    rng = np.random.default_rng(11)
+    X = rng.uniform(-10, 10, (4096, 2))
+    p = native.Problem.from_const(c)
+    if p.get_path() != native.QTET_PATH_SPLIT:
+        pytest.skip("split path not built")
+    a = [t.cpu().numpy() for t in p.loss_grad(X, 1)]
+    p.set_path(native.QTET_PATH_GENERIC)
+    b = [t.cpu().numpy() for t in p.loss_grad(X, 1)]
+    assert np.abs(a[0] - b[0]).max() < 2e-9
+    same = a[2] == b[2]
+    assert same.mean() > 0.999
+    assert (np.abs(a[1] - b[1]) / np.maximum(1, np.abs(b[1]).max(axis=1, keepdims=True)))[same].max() < 1e-7
+    p.close()
