@@ -58,10 +58,13 @@ __global__ void adam_step_kernel(AdamArgs a) {
     }
     a.min_loss[b] = mn;
     a.last_loss[b] = L;
-    const double alpha = lr * a.s2 / a.s1;                   // Keras Adam, t = epoch+1
+    // Explicitly rounded operations (no FMA contraction): the update is bit-identical to the same
+    // expression evaluated in IEEE double on the host, which keeps the (chaotic) trajectories comparable.
+    const double alpha = __ddiv_rn(__dmul_rn(lr, a.s2), a.s1);          // Keras Adam, t = epoch+1
     bool stop = false;
     const bool revert = (L - last >= 0.5) && (L >= 0.5);     // :184
     bool counted_stop = false;
+    const double omb1 = __dsub_rn(1.0, a.beta_1), omb2 = __dsub_rn(1.0, a.beta_2);
     for (int k = 0; k < f; ++k) {
         const long long o = (long long)b * f + k;
         const double x0 = a.xc[i * f + k];
@@ -69,13 +72,13 @@ __global__ void adam_step_kernel(AdamArgs a) {
         if ((a.train_mask >> k) & 1u) {
             const double g = a.grad[i * f + k];
             double m = a.m[o], v = a.v[o];
-            m += (g - m) * (1.0 - a.beta_1);
-            v += (g * g - v) * (1.0 - a.beta_2);
+            m = __dadd_rn(m, __dmul_rn(__dsub_rn(g, m), omb1));
+            v = __dadd_rn(v, __dmul_rn(__dsub_rn(__dmul_rn(g, g), v), omb2));
             a.m[o] = m; a.v[o] = v;
             double denom_v = v;
             if (a.amsgrad) { double vh = fmax(a.vhat[o], v); a.vhat[o] = vh; denom_v = vh; }
-            x1 = x0 - alpha * m / (sqrt(denom_v) + a.epsilon);
-            const double err = fabs(x1 - x0);                // :181
+            x1 = __dsub_rn(x0, __ddiv_rn(__dmul_rn(alpha, m), __dadd_rn(__dsqrt_rn(denom_v), a.epsilon)));
+            const double err = fabs(__dsub_rn(x1, x0));      // :181
             if (!counted_stop && err < a.tol) {              // :202-206 (first offending site returns)
                 const int c = a.err_count[o] + 1;
                 a.err_count[o] = c;

@@ -32,6 +32,8 @@ struct GenericArgs {
     double* grad;
     int* tstar;
     double* trace;
+    const int* list;      // optional: evaluate only points list[0 .. *count)
+    const int* count;
 };
 
 __device__ __forceinline__ double block_sum(double v, double* red, int tid, int nwarps) {
@@ -70,7 +72,9 @@ __global__ void generic_kernel(GenericArgs a) {
     double* mydiag = wdiag + warp * d;
     double* myoff = woff + warp * d;
 
-    for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
+    const long long limit = a.list ? (long long)(*a.count) : a.B;
+    for (long long q = blockIdx.x; q < limit; q += gridDim.x) {
+        const long long b = a.list ? (long long)a.list[q] : q;
         const double* chi = a.chis + b * f;
         __syncthreads();
         // ---------------------------------------------------------------- H build
@@ -354,8 +358,8 @@ size_t generic_smem_bytes(int d, int nthreads) {
     return n * sizeof(double);
 }
 
-int launch_generic(const ProblemView& pv, const double* chis, int64_t B, int site, double* loss,
-                   double* grad, int32_t* tstar, double* trace, cudaStream_t st) {
+static int launch_generic_impl(const ProblemView& pv, const double* chis, int64_t B, const int* list, const int* count,
+                               int site, double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st) {
     if (B <= 0) return QTET_OK;
     if (pv.f > 8) { set_error("generic kernel supports at most 8 sites"); return QTET_EUNSUPPORTED; }
     const int nth = generic_threads(pv.d);
@@ -378,10 +382,23 @@ int launch_generic(const ProblemView& pv, const double* chis, int64_t B, int sit
     GenericArgs a;
     a.pv = pv; a.chis = chis; a.B = B; a.site = site; a.acceptor = (site == pv.f - 1) ? 1 : 0;
     a.ldv = generic_ld(pv.d); a.loss = loss; a.grad = grad; a.tstar = tstar; a.trace = trace;
+    a.list = list; a.count = count;
+    if (list) { grid = 2LL * sms; if (grid > B) grid = B; }
     generic_kernel<<<(unsigned)grid, nth, smem, st>>>(a);
     count_launch();
     QTET_CUDA(cudaGetLastError());
     return QTET_OK;
+}
+
+int launch_generic(const ProblemView& pv, const double* chis, int64_t B, int site, double* loss,
+                   double* grad, int32_t* tstar, double* trace, cudaStream_t st) {
+    return launch_generic_impl(pv, chis, B, nullptr, nullptr, site, loss, grad, tstar, trace, st);
+}
+
+// Evaluate only the points list[0 .. *count) (count read on the device; at most max_count).
+int launch_generic_list(const ProblemView& pv, const double* chis, const int* list, const int* count, long long max_count,
+                        int site, double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st) {
+    return launch_generic_impl(pv, chis, max_count, list, count, site, loss, grad, tstar, trace, st);
 }
 
 int launch_build_h(const ProblemView& pv, const double* chis, double* H, cudaStream_t st) {
