@@ -77,57 +77,77 @@ __global__ void __launch_bounds__(kWarpsA * 32) ql_scalar_kernel(SplitArgs a) {
         unsigned* hdr = a.hdr + pc * kMaxSweeps;
         int pos = 0, ns = 0;
         bool overflow = false;
-        for (int l = 0; l < d && !overflow; ++l) {
-            int iter = 0;
-            while (true) {
-                int m = l;
-                for (; m < d - 1; ++m) {
-                    const double dd = fabs(sd[m * 32 + lane]) + fabs(sd[(m + 1) * 32 + lane]);
-                    if (fabs(se[m * 32 + lane]) <= kEps * dd) break;
+        // bit k of `small`: off[k] is negligible against its diagonal neighbours (bit d-1: sentinel).
+        // Initialised by one scan, then kept current inside the sweeps (only swept entries change).
+        unsigned small = 1u << (d - 1);
+        for (int k = 0; k < d - 1; ++k) {
+            const double dd = fabs(sd[k * 32 + lane]) + fabs(sd[(k + 1) * 32 + lane]);
+            if (fabs(se[k * 32 + lane]) <= kEps * dd) small |= 1u << k;
+        }
+        int l = 0, iter = 0;
+        while (l < d) {
+            const int m = l + __ffs(small >> l) - 1;          // first negligible off-diagonal at or above l
+            if (m == l) { ++l; iter = 0; continue; }
+            if (++iter > 60 || ns >= kMaxSweeps - 1 || pos + (m - l) > a.cap) { overflow = true; break; }
+            if (valid) hdr[ns] = (unsigned)l | ((unsigned)m << 8) | ((unsigned)pos << 16);   // pos < cap < 65536
+            ++ns;
+            const double dl = sd[l * 32 + lane], el = se[l * 32 + lane];
+            double g = (sd[(l + 1) * 32 + lane] - dl) / (2.0 * el);
+            double r = sqrt(fma(g, g, 1.0));
+            g = sd[m * 32 + lane] - dl + el / (g + copysign(r, g));
+            double s = 1.0, c = 1.0, pp = 0.0;
+            double dnext = 0.0;                                // final d[i+2] while finishing plane i
+            int i = m - 1;
+            bool broke = false;
+            for (; i >= l; --i) {
+                const double ei = se[i * 32 + lane];
+                const double fo = s * ei, bo = c * ei;
+                const double r2 = fma(fo, fo, g * g);
+                if (r2 == 0.0) {                               // underflow recovery: finish the sweep with identities
+                    se[(i + 1) * 32 + lane] = 0.0;
+                    sd[(i + 1) * 32 + lane] -= pp;
+                    se[m * 32 + lane] = 0.0;
+                    broke = true;
+                    break;
                 }
-                if (m == l) break;
-                if (++iter > 60 || ns >= kMaxSweeps - 1 || pos + (m - l) > a.cap) { overflow = true; break; }
-                if (valid) hdr[ns] = (unsigned)l | ((unsigned)m << 8);
-                ++ns;
-                const double dl = sd[l * 32 + lane], el = se[l * 32 + lane];
-                double g = (sd[(l + 1) * 32 + lane] - dl) / (2.0 * el);
-                double r = sqrt(fma(g, g, 1.0));
-                g = sd[m * 32 + lane] - dl + el / (g + copysign(r, g));
-                double s = 1.0, c = 1.0, pp = 0.0;
-                int i = m - 1;
-                bool broke = false;
-                for (; i >= l; --i) {
-                    const double ei = se[i * 32 + lane];
-                    const double fo = s * ei, bo = c * ei;
-                    const double r2 = fma(fo, fo, g * g);
-                    if (r2 == 0.0) {                      // underflow recovery: finish the sweep with identities
-                        se[(i + 1) * 32 + lane] = 0.0;
-                        sd[(i + 1) * 32 + lane] -= pp;
-                        se[m * 32 + lane] = 0.0;
-                        broke = true;
-                        break;
-                    }
-                    const double rinv = rsqrt(r2);
-                    r = r2 * rinv;
+                const double rinv = rsqrt(r2);
+                r = r2 * rinv;
+                s = fo * rinv;
+                c = g * rinv;
+                const double di1 = sd[(i + 1) * 32 + lane];
+                g = di1 - pp;
+                const double rr = fma(sd[i * 32 + lane] - g, s, 2.0 * c * bo);
+                pp = s * rr;
+                const double dnew = g + pp;
+                sd[(i + 1) * 32 + lane] = dnew;
+                g = fma(c, rr, -bo);
+                if (i + 1 < m) {                               // off[i+1] = r is final: refresh its flag
                     se[(i + 1) * 32 + lane] = r;
-                    s = fo * rinv;
-                    c = g * rinv;
-                    const double di1 = sd[(i + 1) * 32 + lane];
-                    g = di1 - pp;
-                    r = fma(sd[i * 32 + lane] - g, s, 2.0 * c * bo);
-                    pp = s * r;
-                    sd[(i + 1) * 32 + lane] = g + pp;
-                    g = fma(c, r, -bo);
-                    if (valid) rec[pos] = make_double2(c, s);
-                    ++pos;
+                    const unsigned bit = 1u << (i + 1);
+                    if (r <= kEps * (fabs(dnew) + fabs(dnext))) small |= bit; else small &= ~bit;
                 }
-                if (broke) {
-                    for (; i >= l; --i) { if (valid) rec[pos] = make_double2(1.0, 0.0); ++pos; }
-                    continue;
+                dnext = dnew;
+                if (valid) rec[pos] = make_double2(c, s);
+                ++pos;
+            }
+            if (broke) {
+                for (; i >= l; --i) { if (valid) rec[pos] = make_double2(1.0, 0.0); ++pos; }
+                // rare path: rebuild the flags from scratch
+                small = 1u << (d - 1);
+                for (int k = 0; k < d - 1; ++k) {
+                    const double dd = fabs(sd[k * 32 + lane]) + fabs(sd[(k + 1) * 32 + lane]);
+                    if (fabs(se[k * 32 + lane]) <= kEps * dd) small |= 1u << k;
                 }
-                sd[l * 32 + lane] -= pp;
-                se[l * 32 + lane] = g;
-                se[m * 32 + lane] = 0.0;
+                continue;
+            }
+            const double dlnew = sd[l * 32 + lane] - pp;
+            sd[l * 32 + lane] = dlnew;
+            se[l * 32 + lane] = g;
+            se[m * 32 + lane] = 0.0;
+            small |= 1u << m;
+            {
+                const unsigned bit = 1u << l;
+                if (fabs(g) <= kEps * (fabs(dlnew) + fabs(dnext))) small |= bit; else small &= ~bit;
             }
         }
         if (valid) {
@@ -154,18 +174,29 @@ __device__ __forceinline__ double fast_rcp(double x) {
     return r;
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kRing = 4;                   // sweeps of rotation records in flight per warp
+
 template <int D>
-__global__ void __launch_bounds__(kWarpsB * 32) apply_kernel(SplitArgs a, int smem_per_warp_doubles) {
+__global__ void __launch_bounds__(kWarpsB * 32, 5) apply_kernel(SplitArgs a, int smem_per_warp_doubles) {
     extern __shared__ double sm[];
     const ProblemView& pv = a.pv;
     const int d = pv.d, f = pv.f, T = pv.T;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* base = sm + (size_t)warp * smem_per_warp_doubles;
-    double2* rbuf = reinterpret_cast<double2*>(base);          // [2][32]  staged rotations by plane index
-    double2* zbuf = rbuf + 64;                                  // [2][32]  z_i = c_i f_i^k
+    double2* rbuf = reinterpret_cast<double2*>(base);          // [kRing][32]  staged rotations by plane index
+    double2* zbuf = rbuf + kRing * 32;                          // [2][32]  z_i = c_i f_i^k                                  // [2][32]  z_i = c_i f_i^k
     double* lanev = reinterpret_cast<double*>(zbuf + 64);       // [8][32]  per-eigen-index vectors for the gradient
-    double* U = lanev + 8 * 32;                                 // union: p[T][33] | V^T staging [32][33] | S packed
-    constexpr int LDU = 33;
+    unsigned* hbuf = reinterpret_cast<unsigned*>(lanev + 8 * 32);   // [kMaxSweeps + kRing] sweep headers
+    double* U = lanev + 8 * 32 + (kMaxSweeps + 8) / 2;                                 // union: p[T][LDU] | V^T staging [D][LDU] | S packed
+    constexpr int LDU = D | 1;                                  // odd row pitch: conflict-free column reads
 
     const double wsite = (lane < d) ? pv.occ[lane * f + a.site] : 0.0;
     const double dt = (T > 1) ? pv.tgrid[1] : 0.0;
@@ -178,45 +209,57 @@ __global__ void __launch_bounds__(kWarpsB * 32) apply_kernel(SplitArgs a, int sm
 #pragma unroll
         for (int k = 0; k < D; ++k) v[k] = (k == lane) ? 1.0 : 0.0;
 
-        // ---- replay the rotation stream
-        auto header = [&](int s) -> unsigned {
-            const unsigned h = (s < 32) ? H0 : (s < 64) ? H1 : (s < 96) ? H2 : H3;
-            return __shfl_sync(0xffffffffu, h, s & 31);
+        // ---- replay the rotation stream.  Records travel global -> shared with cp.async, kRing-1 sweeps
+        // ahead of their use (each lane copies one record of a sweep straight to its plane slot), so the
+        // HBM/L2 latency of the stream is off the critical path.  Sweep headers (l | m<<8 | pos<<16) are
+        // staged in shared memory once per point.
+        hbuf[lane] = H0; hbuf[32 + lane] = H1; hbuf[64 + lane] = H2; hbuf[96 + lane] = H3;
+        if (lane < kRing) hbuf[kMaxSweeps + lane] = kTerm;
+        __syncwarp();
+        auto issue = [&](int s) {
+            const unsigned hh = hbuf[s];
+            if (hh != kTerm) {
+                const int li = hh & 0xff, mi = (hh >> 8) & 0xff, pi = hh >> 16;
+                if (lane < mi - li) cp_async16(rbuf + (s % kRing) * 32 + (mi - 1 - lane), rec + pi + lane);
+            }
+            cp_async_commit();
         };
-        int pos = 0;
-        unsigned h = header(0);
-        double2 cur = make_double2(1.0, 0.0);
-        if (h != kTerm) {
-            const int l0 = h & 0xff, m0 = (h >> 8) & 0xff;
-            if (lane < m0 - l0) cur = rec[lane];
-        }
+#pragma unroll
+        for (int s = 0; s < kRing - 1; ++s) issue(s);
+        unsigned h = hbuf[0];
         for (int s = 0; h != kTerm; ++s) {
             const int l = h & 0xff, m = (h >> 8) & 0xff;
-            const int cnt = m - l;
-            const unsigned hn = header(s + 1);
-            double2 nxt = make_double2(1.0, 0.0);
-            const int posn = pos + cnt;
-            if (hn != kTerm) {
-                const int ln = hn & 0xff, mn = (hn >> 8) & 0xff;
-                if (lane < mn - ln) nxt = rec[posn + lane];
-            }
-            double2* rb = rbuf + (s & 1) * 32;
-            if (lane < cnt) rb[m - 1 - lane] = cur;         // record j of the sweep acts on plane m-1-j
+            __syncwarp();                                   // everyone is done with the slot about to be refilled
+            issue(s + kRing - 1);
+            h = hbuf[s + 1];
+            cp_async_wait<kRing - 1>();                     // this lane's records of sweep s have landed
+            double2* rb = rbuf + (s % kRing) * 32;
+            // identity outside the window [l, m): above an interior split, and below l down to the group edge
+            if (lane < D - 1 && (lane >= m || lane < l)) rb[lane] = make_double2(1.0, 0.0);
             __syncwarp();
-            bool active = false;
+            // Planes D-2 .. l, top-down, in groups of four with ONE warp-uniform exit test per group (QL
+            // deflates from the top, so the window is almost always the suffix [l, d-2]).  Inside a group the
+            // code is branch-free: the four (c, s) loads are issued ahead of the dependent chain and only one
+            // fma per plane sits on that chain:  v[i] <- c x - s y  with  c x  computed off-chain.
 #pragma unroll
-            for (int i = D - 2; i >= 0; --i) {
-                if (i == m - 1) active = true;
-                if (active) {
-                    const double2 cs = rb[i];
-                    const double x = v[i], y = v[i + 1];
-                    v[i + 1] = fma(cs.y, x, cs.x * y);
-                    v[i] = fma(cs.x, x, -(cs.y * y));
+            for (int i0 = D - 2; i0 >= 0; i0 -= 4) {
+                if (i0 < l) break;
+                double2 cs[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) cs[k] = rb[(i0 - k >= 0) ? (i0 - k) : 0];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = i0 - k;
+                    if (i >= 0) {
+                        const double x = v[i], y = v[i + 1];
+                        const double t1 = cs[k].x * x, t2 = cs[k].y * x;
+                        v[i] = fma(-cs[k].y, y, t1);
+                        v[i + 1] = fma(cs[k].x, y, t2);
+                    }
                 }
-                if (i == l) active = false;
             }
-            cur = nxt; pos = posn; h = hn;
         }
+        cp_async_wait<0>();
 
         // ---- c = V[0,:], eigenvalues, unit phase step w = exp(-i e dt)
         __syncwarp();
@@ -245,19 +288,15 @@ __global__ void __launch_bounds__(kWarpsB * 32) apply_kernel(SplitArgs a, int sm
             double2* zb = zbuf + (k & 1) * 32;
             zb[lane] = make_double2(zr, zi);
             __syncwarp();
-            double pr0 = 0.0, pi0 = 0.0, pr1 = 0.0, pi1 = 0.0;
+            double ar4[4] = {0.0, 0.0, 0.0, 0.0}, ai4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-            for (int i = 0; i + 1 < D; i += 2) {
-                const double2 z0 = zb[i], z1 = zb[i + 1];
-                pr0 = fma(v[i], z0.x, pr0); pi0 = fma(v[i], z0.y, pi0);
-                pr1 = fma(v[i + 1], z1.x, pr1); pi1 = fma(v[i + 1], z1.y, pi1);
+            for (int i = 0; i < D; ++i) {
+                const double2 z0 = zb[i];
+                ar4[i & 3] = fma(v[i], z0.x, ar4[i & 3]);
+                ai4[i & 3] = fma(v[i], z0.y, ai4[i & 3]);
             }
-            if (D & 1) {
-                const double2 z0 = zb[D - 1];
-                pr0 = fma(v[D - 1], z0.x, pr0); pi0 = fma(v[D - 1], z0.y, pi0);
-            }
-            const double pr = pr0 + pr1, pi = pi0 + pi1;
-            U[k * LDU + lane] = wsite * fma(pr, pr, pi * pi);
+            const double pr = (ar4[0] + ar4[1]) + (ar4[2] + ar4[3]), pi = (ai4[0] + ai4[1]) + (ai4[2] + ai4[3]);
+            if (lane < D) U[k * LDU + lane] = wsite * fma(pr, pr, pi * pi);
             const double nr = fma(zr, wre, -(zi * wim));
             zi = fma(zr, wim, zi * wre);
             zr = nr;
@@ -312,13 +351,16 @@ __global__ void __launch_bounds__(kWarpsB * 32) apply_kernel(SplitArgs a, int sm
         // w conj(psi) per row, then a = V^T (w conj psi) through a transposed copy of V in shared memory
         double2* wc = zbuf + 32;
         wc[lane] = make_double2(wsite * pr, -wsite * pi);
+        if (lane < D) {
 #pragma unroll
-        for (int i = 0; i < D; ++i) U[lane * LDU + i] = v[i];
+            for (int i = 0; i < D; ++i) U[lane * LDU + i] = v[i];
+        }
         __syncwarp();
         double ar = 0.0, ai = 0.0;
+        const int lcol = (lane < D) ? lane : 0;
 #pragma unroll
         for (int j = 0; j < D; ++j) {
-            const double vt = U[j * LDU + lane];          // V[j][lane]
+            const double vt = U[j * LDU + lcol];          // V[j][lane]
             const double2 w = wc[j];
             ar = fma(vt, w.x, ar); ai = fma(vt, w.y, ai);
         }
@@ -383,14 +425,15 @@ __global__ void __launch_bounds__(kWarpsB * 32) apply_kernel(SplitArgs a, int sm
 template <int D>
 int launch_apply(const SplitArgs& a, int sms, cudaStream_t st) {
     const int T = a.pv.T;
-    const int urows = (T > 32) ? T : 32;
-    int udoubles = urows * 33;
+    const int urows = (T > D) ? T : D;
+    int udoubles = urows * (D | 1);
     const int need_s = 32 + D * (D - 1) / 2;
     if (need_s > udoubles) udoubles = need_s;
     udoubles = (udoubles + 1) & ~1;
-    const int per_warp = 128 + 128 + 8 * 32 + udoubles;
+    const int per_warp = 2 * kRing * 32 + 128 + 8 * 32 + (kMaxSweeps + 8) / 2 + udoubles;
     const size_t smem = (size_t)per_warp * kWarpsB * sizeof(double);
     QTET_CUDA(cudaFuncSetAttribute(apply_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QTET_CUDA(cudaFuncSetAttribute(apply_kernel<D>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int per_sm = 0;
     QTET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, apply_kernel<D>, kWarpsB * 32, smem));
     if (per_sm < 1) per_sm = 1;
@@ -415,10 +458,12 @@ struct SplitWorkspace {
     int device = 0, sms = 0;
     int cap = 0, D = 0;
     long long chunk = 0;
-    char* blob = nullptr;
+    char* blob = nullptr;            // two chunk buffers (double-buffered between K_A and K_B)
     size_t blob_bytes = 0;
     unsigned short* pair_tab = nullptr;
-    int* overflow_count = nullptr;   // [1]
+    int* overflow_count = nullptr;   // [2]
+    cudaStream_t aux = nullptr;      // K_A runs here, one chunk ahead of K_B on the caller's stream
+    cudaEvent_t ev_fork = nullptr, ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr};
 };
 
 bool split_eligible(const ProblemView& pv) {
@@ -430,12 +475,21 @@ void split_workspace_free(SplitWorkspace* ws) {
     if (ws->blob) cudaFree(ws->blob);
     if (ws->pair_tab) cudaFree(ws->pair_tab);
     if (ws->overflow_count) cudaFree(ws->overflow_count);
+    if (ws->aux) cudaStreamDestroy(ws->aux);
+    if (ws->ev_fork) cudaEventDestroy(ws->ev_fork);
+    for (int i = 0; i < 2; ++i) {
+        if (ws->ev_a[i]) cudaEventDestroy(ws->ev_a[i]);
+        if (ws->ev_b[i]) cudaEventDestroy(ws->ev_b[i]);
+    }
     delete ws;
 }
 
 // generic kernel restricted to an index list (qtet_generic.cu)
 int launch_generic_list(const ProblemView& pv, const double* chis, const int* list, const int* count, long long max_count,
                         int site, double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st);
+
+template <int D>
+static int apply_dispatch(const SplitArgs& a, int sms, cudaStream_t st) { return launch_apply<D>(a, sms, st); }
 
 int launch_split(const ProblemView& pv, SplitWorkspace** wsp, const double* chis, int64_t B, int site,
                  double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st) {
@@ -445,6 +499,7 @@ int launch_split(const ProblemView& pv, SplitWorkspace** wsp, const double* chis
     const int d = pv.d;
     if (!ws) {
         ws = new SplitWorkspace();
+        *wsp = ws;
         QTET_CUDA(cudaGetDevice(&ws->device));
         QTET_CUDA(cudaDeviceGetAttribute(&ws->sms, cudaDevAttrMultiProcessorCount, ws->device));
         ws->D = padded_dim(d);
@@ -455,22 +510,31 @@ int launch_split(const ProblemView& pv, SplitWorkspace** wsp, const double* chis
         if (tab.empty()) tab.push_back(0);
         QTET_CUDA(cudaMalloc(&ws->pair_tab, tab.size() * sizeof(unsigned short)));
         QTET_CUDA(cudaMemcpy(ws->pair_tab, tab.data(), tab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
-        QTET_CUDA(cudaMalloc(&ws->overflow_count, sizeof(int)));
-        *wsp = ws;
+        QTET_CUDA(cudaMalloc(&ws->overflow_count, 2 * sizeof(int)));
+        QTET_CUDA(cudaStreamCreateWithFlags(&ws->aux, cudaStreamNonBlocking));
+        QTET_CUDA(cudaEventCreateWithFlags(&ws->ev_fork, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) {
+            QTET_CUDA(cudaEventCreateWithFlags(&ws->ev_a[i], cudaEventDisableTiming));
+            QTET_CUDA(cudaEventCreateWithFlags(&ws->ev_b[i], cudaEventDisableTiming));
+        }
     }
-    // per-point workspace: rotation stream + headers + eigenvalues + overflow slot
+    // per-point workspace: rotation stream + sweep headers + eigenvalues + overflow slot
     const size_t per_point = (size_t)ws->cap * sizeof(double2) + kMaxSweeps * sizeof(unsigned) + (size_t)d * 8 + 4;
-    long long chunk = (long long)((size_t)3 << 30) / (long long)per_point;       // <= 3 GiB of streams in flight
-    chunk = (chunk / 4096) * 4096;
-    if (chunk < 4096) chunk = 4096;
+    // chunking: two buffers in flight; aim for >= 8 chunks on big batches so that K_A(c+1) overlaps K_B(c),
+    // but keep chunks large enough to fill the machine several times over
+    long long chunk = (long long)((size_t)4 << 30) / (long long)per_point;      // <= 4 GiB per buffer
+    long long want = (B + 3) / 4;
+    if (want < 131072) want = 131072;
+    if (chunk > want) chunk = want;
+    chunk = ((chunk + 4095) / 4096) * 4096;
     if (chunk > B) chunk = ((B + 31) / 32) * 32;
-    const size_t o_stream = 0;
-    const size_t o_hdr = o_stream + (size_t)chunk * ws->cap * sizeof(double2);
+    const size_t o_hdr = (size_t)chunk * ws->cap * sizeof(double2);
     const size_t o_ev = o_hdr + (size_t)chunk * kMaxSweeps * sizeof(unsigned);
     const size_t o_list = o_ev + (((size_t)chunk * d * 8 + 255) / 256) * 256;
-    const size_t total = o_list + (size_t)chunk * 4 + 256;
+    const size_t buf_bytes = ((o_list + (size_t)chunk * 4 + 255) / 256) * 256;
+    const size_t total = 2 * buf_bytes;
     if (total > ws->blob_bytes) {
-        if (ws->blob) cudaFree(ws->blob);
+        if (ws->blob) { cudaDeviceSynchronize(); cudaFree(ws->blob); }
         ws->blob = nullptr; ws->blob_bytes = 0;
         cudaError_t e = cudaMalloc(&ws->blob, total);
         if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(split workspace) failed"); return QTET_ENOMEM; }
@@ -480,45 +544,59 @@ int launch_split(const ProblemView& pv, SplitWorkspace** wsp, const double* chis
 
     SplitArgs a;
     a.pv = pv; a.site = site; a.acceptor = (site == pv.f - 1) ? 1 : 0; a.cap = ws->cap;
-    a.stream = (double2*)(ws->blob + o_stream); a.hdr = (unsigned*)(ws->blob + o_hdr);
-    a.ev = (double*)(ws->blob + o_ev); a.overflow_list = (int*)(ws->blob + o_list);
-    a.overflow_count = ws->overflow_count; a.pair_tab = ws->pair_tab;
+    a.pair_tab = ws->pair_tab;
 
     const size_t smemA = (size_t)kWarpsA * 2 * d * 32 * sizeof(double);
     QTET_CUDA(cudaFuncSetAttribute(ql_scalar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+    QTET_CUDA(cudaFuncSetAttribute(ql_scalar_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int per_sm_a = 0;
     QTET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, ql_scalar_kernel, kWarpsA * 32, smemA));
     if (per_sm_a < 1) per_sm_a = 1;
 
-    for (long long lo = 0; lo < B; lo += chunk) {
+    // fork: the auxiliary stream starts after everything already queued on the caller's stream
+    QTET_CUDA(cudaEventRecord(ws->ev_fork, st));
+    QTET_CUDA(cudaStreamWaitEvent(ws->aux, ws->ev_fork, 0));
+    int c = 0;
+    for (long long lo = 0; lo < B; lo += chunk, ++c) {
+        const int buf = c & 1;
+        char* base = ws->blob + (size_t)buf * buf_bytes;
         const long long n = (B - lo < chunk) ? (B - lo) : chunk;
+        a.stream = (double2*)base; a.hdr = (unsigned*)(base + o_hdr);
+        a.ev = (double*)(base + o_ev); a.overflow_list = (int*)(base + o_list);
+        a.overflow_count = ws->overflow_count + buf;
         a.chis = chis + lo * pv.f; a.n = n;
         a.loss = loss ? loss + lo : nullptr;
         a.grad = grad ? grad + lo * pv.f : nullptr;
         a.tstar = tstar ? tstar + lo : nullptr;
         a.trace = trace ? trace + lo * pv.T : nullptr;
-        QTET_CUDA(cudaMemsetAsync(ws->overflow_count, 0, sizeof(int), st));
+        // K_A(c) on aux, after K_B(c-2) released this buffer
+        if (c >= 2) QTET_CUDA(cudaStreamWaitEvent(ws->aux, ws->ev_b[buf], 0));
+        QTET_CUDA(cudaMemsetAsync(a.overflow_count, 0, sizeof(int), ws->aux));
         long long gridA = (long long)ws->sms * per_sm_a;
         const long long needA = ((n + 31) / 32 + kWarpsA - 1) / kWarpsA;
         if (gridA > needA) gridA = needA;
-        ql_scalar_kernel<<<(unsigned)gridA, kWarpsA * 32, smemA, st>>>(a);
+        ql_scalar_kernel<<<(unsigned)gridA, kWarpsA * 32, smemA, ws->aux>>>(a);
         count_launch();
         QTET_CUDA(cudaGetLastError());
+        QTET_CUDA(cudaEventRecord(ws->ev_a[buf], ws->aux));
+        // K_B(c) on the caller's stream
+        QTET_CUDA(cudaStreamWaitEvent(st, ws->ev_a[buf], 0));
         int rc;
         switch (ws->D) {
-            case 4: rc = launch_apply<4>(a, ws->sms, st); break;
-            case 6: rc = launch_apply<6>(a, ws->sms, st); break;
-            case 8: rc = launch_apply<8>(a, ws->sms, st); break;
-            case 12: rc = launch_apply<12>(a, ws->sms, st); break;
-            case 16: rc = launch_apply<16>(a, ws->sms, st); break;
-            case 21: rc = launch_apply<21>(a, ws->sms, st); break;
-            case 24: rc = launch_apply<24>(a, ws->sms, st); break;
-            default: rc = launch_apply<32>(a, ws->sms, st); break;
+            case 4: rc = apply_dispatch<4>(a, ws->sms, st); break;
+            case 6: rc = apply_dispatch<6>(a, ws->sms, st); break;
+            case 8: rc = apply_dispatch<8>(a, ws->sms, st); break;
+            case 12: rc = apply_dispatch<12>(a, ws->sms, st); break;
+            case 16: rc = apply_dispatch<16>(a, ws->sms, st); break;
+            case 21: rc = apply_dispatch<21>(a, ws->sms, st); break;
+            case 24: rc = apply_dispatch<24>(a, ws->sms, st); break;
+            default: rc = apply_dispatch<32>(a, ws->sms, st); break;
         }
         if (rc) return rc;
         // overflowed points (if any) are recomputed by the fused generic kernel
-        rc = launch_generic_list(pv, a.chis, a.overflow_list, ws->overflow_count, n, site, a.loss, a.grad, a.tstar, a.trace, st);
+        rc = launch_generic_list(pv, a.chis, a.overflow_list, a.overflow_count, n, site, a.loss, a.grad, a.tstar, a.trace, st);
         if (rc) return rc;
+        QTET_CUDA(cudaEventRecord(ws->ev_b[buf], st));
     }
     return QTET_OK;
 }
