@@ -11,8 +11,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "lib", "libqtet_b200.so")
+# debug variants: QTET_NVCC_DEFS="-DQTET_PHASE_TIMING" QTET_LIB_SUFFIX=_dbg python build_native.py
+SUFFIX = os.environ.get("QTET_LIB_SUFFIX", "")
+EXTRA = os.environ.get("QTET_NVCC_DEFS", "").split()
+OBJ = os.path.join(HERE, "build" + SUFFIX)
+LIB = os.path.join(HERE, "lib", f"libqtet_b200{SUFFIX}.so")
 SOURCES = ["qtet_capi.cu", "qtet_generic.cu", "qtet_split.cu", "qtet_adam.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -44,7 +47,7 @@ def build(force=False, verbose=False):
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc, *ARCH, *FLAGS, "-c", s, "-o", o]
+            cmd = [nvcc, *ARCH, *FLAGS, *EXTRA, "-c", s, "-o", o]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), flush=True)

@@ -3,18 +3,23 @@
 //
 // The eigendecomposition is split by the kind of parallelism it offers:
 //
-//   ql_scalar_kernel  (K_A)  one THREAD per parameter point.  Implicit-shift QL on the tridiagonal
-//                     (diag, off) only -- O(d^2) scalar work with sqrt/div chains that would waste a
-//                     whole warp if done per warp.  Emits the eigenvalues and the sequence of plane
-//                     rotations (c, s), sweep by sweep, into a per-point stream in HBM/L2.
-//   apply_kernel      (K_B)  one WARP per parameter point, lane j owns row j of V in REGISTERS.
-//                     Replays the rotation stream on V = I (4 DFMA per rotation per lane, the
-//                     O(d^3) part), then the time evolution psi = V (c . exp(-i e t)) with phases
-//                     advanced by a complex rotation recurrence, <n(t)>, the loss, and the analytic
-//                     gradient through the symmetrised Daleckii-Krein kernel.
+//   ql_scalar_kernel (K_A)  one THREAD per parameter point, a warp = a BATCH of 32 points.
+//        Implicit-shift QL on the tridiagonal (diag, off) only: O(d^2) scalar work with rsqrt/div
+//        chains that would waste a whole warp if done per warp.  The warp advances in lock-step
+//        ROUNDS (one QL sweep per still-active lane), so that the plane rotations (c, s) it emits
+//        form a stream  rec[batch][iteration][lane]  written with fully coalesced 512 B rows, and
+//        one header word per (round, lane) says which planes [l, m) the lane swept and where the
+//        round starts in the stream.
+//   apply_kernel (K_B)  G lanes per parameter point (32/G points of one batch per warp), every lane
+//        owning R = ceil(D/G) rows of V in REGISTERS.  Replays the rounds on V = I -- four FP64
+//        instructions per row and plane, R independent dependency chains per lane, (c, s) fetched
+//        once per plane and point from a cp.async-fed shared-memory ring -- then the time evolution
+//        psi = V (c . exp(-i e t)) with phases advanced by a complex rotation recurrence, <n(t)>,
+//        the loss, and the analytic gradient through the symmetrised Daleckii-Krein kernel.
 //
-// Points whose stream overflows its slot (pathological convergence) are appended to a list and
-// recomputed by the fused generic kernel; no host synchronisation is involved.
+// Batches whose stream overflows its slot (pathological convergence) are appended to a list and
+// recomputed by the fused generic kernel; no host synchronisation is involved.  K_A runs one chunk
+// ahead of K_B on an auxiliary stream.
 #include "qtet_common.cuh"
 
 namespace qtet {
@@ -22,149 +27,179 @@ namespace qtet {
 namespace {
 
 constexpr double kEps = 1.1102230246251565e-16;
-constexpr int kMaxSweeps = 128;            // header slots per point
-constexpr unsigned kTerm = 0xffffffffu;
+constexpr int kMaxRounds = 128;            // header rows per batch
 constexpr int kWarpsA = 4;                 // warps per CTA, scalar kernel
-constexpr int kWarpsB = 4;                 // warps per CTA, apply kernel
+constexpr int kRing = 4;                   // rounds of rotation records in flight per warp (K_B)
+constexpr unsigned kIdle = 0xffffu;        // l = m = 0xff : lane takes no part in the round
 
 struct SplitArgs {
     ProblemView pv;
     const double* chis;       // [n, f] (already offset to the chunk)
     long long n;              // points in this chunk
     int site, acceptor;
-    int cap;                  // rotation records per point
-    double2* stream;          // [n, cap]
-    unsigned* hdr;            // [n, kMaxSweeps]
-    double* ev;               // [n, d]
+    int capit;                // stream rows (warp iterations) per batch
+    double2* stream;          // [nb][capit][32]
+    unsigned* hdr;            // [nb][kMaxRounds][32]   l | m << 8 | it0 << 16
+    int* nrounds;             // [nb]
+    double* ev;               // [n, d]  eigenvalues (shifted by the mean of the diagonal)
     int* overflow_list;       // [n]
     int* overflow_count;      // [1]
     const unsigned short* pair_tab;   // [D(D-1)/2] i | j << 8
     double* loss; double* grad; int* tstar; double* trace;   // chunk-offset outputs
 };
 
+__device__ __forceinline__ unsigned lowmask(int l) { return (l >= 32) ? 0xffffffffu : ((1u << l) - 1u); }
+
 // ------------------------------------------------------------------------------------------------
-// K_A: thread-per-point scalar QL.  diag/off live in shared memory as [k][lane] (bank = lane, so
-// lanes may sit at different k without conflicts).
+// K_A: thread-per-point scalar QL in warp-synchronous rounds.  diag/off live in shared memory as
+// [2k + {0,1}][lane] (bank = lane: lanes may sit at different k without conflicts).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kWarpsA * 32) ql_scalar_kernel(SplitArgs a) {
     extern __shared__ double sm[];
     const ProblemView& pv = a.pv;
     const int d = pv.d, f = pv.f;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* sd = sm + (size_t)warp * 2 * d * 32;
-    double* se = sd + d * 32;
+    double* arr = sm + (size_t)warp * 2 * d * 32 + lane;     // diag k at arr[64 k], off k at arr[64 k + 32]
     const long long nbatch = (a.n + 31) / 32;
+    const unsigned below_top = lowmask(d - 1);
     for (long long batch = (long long)blockIdx.x * kWarpsA + warp; batch < nbatch; batch += (long long)gridDim.x * kWarpsA) {
         const long long p = batch * 32 + lane;
         const bool valid = p < a.n;
         const long long pc = valid ? p : a.n - 1;
         // ---- H build (HamiltonianLoss.py:131-134) + global-phase shift by the mean of the diagonal
+        double hchi[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hchi[k] = (k < f) ? 0.5 * a.chis[pc * f + k] : 0.0;
         double mean = 0.0;
         for (int m = 0; m < d; ++m) {
             double acc = 0.0;
-            for (int k = 0; k < f; ++k) {
-                const double n = pv.occ[m * f + k];
-                acc = acc + (pv.omegas[k] * n + (0.5 * a.chis[pc * f + k]) * (n * n));
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (k < f) {
+                    const double n = pv.occ[m * f + k];
+                    acc = acc + (pv.omegas[k] * n + hchi[k] * (n * n));
+                }
             }
-            sd[m * 32 + lane] = acc;
-            se[m * 32 + lane] = (m < d - 1) ? pv.offd[m] : 0.0;
+            arr[64 * m] = acc;
+            arr[64 * m + 32] = (m < d - 1) ? pv.offd[m] : 0.0;
             mean += acc;
         }
         mean /= (double)d;
-        for (int m = 0; m < d; ++m) sd[m * 32 + lane] -= mean;
+        for (int m = 0; m < d; ++m) arr[64 * m] -= mean;
 
-        double2* rec = a.stream + pc * a.cap;
-        unsigned* hdr = a.hdr + pc * kMaxSweeps;
-        int pos = 0, ns = 0;
-        bool overflow = false;
+        double2* rec = a.stream + (size_t)batch * a.capit * 32 + lane;
+        unsigned* hdr = a.hdr + (size_t)batch * kMaxRounds * 32 + lane;
         // bit k of `small`: off[k] is negligible against its diagonal neighbours (bit d-1: sentinel).
         // Initialised by one scan, then kept current inside the sweeps (only swept entries change).
         unsigned small = 1u << (d - 1);
         for (int k = 0; k < d - 1; ++k) {
-            const double dd = fabs(sd[k * 32 + lane]) + fabs(sd[(k + 1) * 32 + lane]);
-            if (fabs(se[k * 32 + lane]) <= kEps * dd) small |= 1u << k;
+            const double dd = fabs(arr[64 * k]) + fabs(arr[64 * k + 64]);
+            if (fabs(arr[64 * k + 32]) <= kEps * dd) small |= 1u << k;
         }
-        int l = 0, iter = 0;
-        while (l < d) {
-            const int m = l + __ffs(small >> l) - 1;          // first negligible off-diagonal at or above l
-            if (m == l) { ++l; iter = 0; continue; }
-            if (++iter > 60 || ns >= kMaxSweeps - 1 || pos + (m - l) > a.cap) { overflow = true; break; }
-            if (valid) hdr[ns] = (unsigned)l | ((unsigned)m << 8) | ((unsigned)pos << 16);   // pos < cap < 65536
-            ++ns;
-            const double dl = sd[l * 32 + lane], el = se[l * 32 + lane];
-            double g = (sd[(l + 1) * 32 + lane] - dl) / (2.0 * el);
-            double r = sqrt(fma(g, g, 1.0));
-            g = sd[m * 32 + lane] - dl + el / (g + copysign(r, g));
-            double s = 1.0, c = 1.0, pp = 0.0;
-            double dnext = 0.0;                                // final d[i+2] while finishing plane i
-            int i = m - 1;
+        int it = 0, round = 0, l = 0, iter = 0;
+        bool overflow = false;
+        while (true) {
+            // first index >= l whose off-diagonal is still alive; none -> this lane is finished
+            const unsigned alive = (~small) & below_top & ~lowmask(l);
+            const bool done = (alive == 0u);
+            const int lnew = done ? d : (__ffs(alive) - 1);
+            if (lnew != l) iter = 0;
+            l = lnew;
+            if (__all_sync(0xffffffffu, done)) break;
+            const int m = done ? l : (l + __ffs(small >> l) - 1);      // first negligible off-diagonal above l
+            ++iter;
+            const int cnt = done ? 0 : (m - l);
+            const int maxcnt = __reduce_max_sync(0xffffffffu, cnt);
+            if (__any_sync(0xffffffffu, !done && iter > 60) || round >= kMaxRounds - 1 || it + maxcnt > a.capit) {
+                overflow = true;
+                break;
+            }
+            hdr[round * 32] = done ? (kIdle | ((unsigned)it << 16)) : ((unsigned)l | ((unsigned)m << 8) | ((unsigned)it << 16));
+            double g = 0.0, s = 1.0, c = 1.0, pp = 0.0, dnext = 0.0;
+            if (!done) {                                   // Wilkinson shift from the leading 2x2 of the block
+                const double dl = arr[64 * l], el = arr[64 * l + 32];
+                const double gg = (arr[64 * l + 64] - dl) / (2.0 * el);
+                const double rr = sqrt(fma(gg, gg, 1.0));
+                g = arr[64 * m] - dl + el / (gg + copysign(rr, gg));
+            }
             bool broke = false;
-            for (; i >= l; --i) {
-                const double ei = se[i * 32 + lane];
-                const double fo = s * ei, bo = c * ei;
-                const double r2 = fma(fo, fo, g * g);
-                if (r2 == 0.0) {                               // underflow recovery: finish the sweep with identities
-                    se[(i + 1) * 32 + lane] = 0.0;
-                    sd[(i + 1) * 32 + lane] -= pp;
-                    se[m * 32 + lane] = 0.0;
-                    broke = true;
-                    break;
+            int i = done ? 0 : (m - 1);
+            // software-pipelined operands of the first plane: e[i], d[i], d[i+1]
+            double ei = arr[64 * i + 32], di = arr[64 * i], di1 = arr[64 * i + 64];
+            for (int j = 0; j < maxcnt; ++j) {
+                if (j < cnt && !broke) {
+                    // operands of the next plane, fetched before this plane's stores
+                    const int inx = (i > l) ? (i - 1) : i;
+                    const double ei_n = arr[64 * inx + 32];
+                    const double di_n = arr[64 * inx];
+                    const double fo = s * ei, bo = c * ei;
+                    const double r2 = fma(fo, fo, g * g);
+                    if (r2 == 0.0) {                       // underflow recovery: the rest of the sweep is identity
+                        arr[64 * (i + 1) + 32] = 0.0;
+                        arr[64 * (i + 1)] = di1 - pp;
+                        arr[64 * m + 32] = 0.0;
+                        broke = true;
+                        if (valid) rec[(size_t)(it + j) * 32] = make_double2(1.0, 0.0);
+                    } else {
+                        const double rinv = rsqrt(r2);
+                        const double r = r2 * rinv;
+                        s = fo * rinv;
+                        c = g * rinv;
+                        g = di1 - pp;
+                        const double rr = fma(di - g, s, 2.0 * c * bo);
+                        pp = s * rr;
+                        const double dnew = g + pp;
+                        arr[64 * (i + 1)] = dnew;
+                        g = fma(c, rr, -bo);
+                        if (i + 1 < m) {                   // off[i+1] = r is final: refresh its flag
+                            arr[64 * (i + 1) + 32] = r;
+                            const unsigned bit = 1u << (i + 1);
+                            if (r <= kEps * (fabs(dnew) + fabs(dnext))) small |= bit; else small &= ~bit;
+                        }
+                        dnext = dnew;
+                        if (valid) rec[(size_t)(it + j) * 32] = make_double2(c, s);
+                        // the next plane's d[i+1] is this plane's (untouched) d[i]
+                        di1 = di; di = di_n; ei = ei_n;
+                        --i;
+                    }
+                } else if (j < cnt) {
+                    if (valid) rec[(size_t)(it + j) * 32] = make_double2(1.0, 0.0);
                 }
-                const double rinv = rsqrt(r2);
-                r = r2 * rinv;
-                s = fo * rinv;
-                c = g * rinv;
-                const double di1 = sd[(i + 1) * 32 + lane];
-                g = di1 - pp;
-                const double rr = fma(sd[i * 32 + lane] - g, s, 2.0 * c * bo);
-                pp = s * rr;
-                const double dnew = g + pp;
-                sd[(i + 1) * 32 + lane] = dnew;
-                g = fma(c, rr, -bo);
-                if (i + 1 < m) {                               // off[i+1] = r is final: refresh its flag
-                    se[(i + 1) * 32 + lane] = r;
-                    const unsigned bit = 1u << (i + 1);
-                    if (r <= kEps * (fabs(dnew) + fabs(dnext))) small |= bit; else small &= ~bit;
+            }
+            it += maxcnt;
+            if (!done) {
+                if (broke) {                               // rare path: rebuild the flags from scratch
+                    small = 1u << (d - 1);
+                    for (int k = 0; k < d - 1; ++k) {
+                        const double dd = fabs(arr[64 * k]) + fabs(arr[64 * k + 64]);
+                        if (fabs(arr[64 * k + 32]) <= kEps * dd) small |= 1u << k;
+                    }
+                } else {
+                    const double dlnew = arr[64 * l] - pp;
+                    arr[64 * l] = dlnew;
+                    arr[64 * l + 32] = g;
+                    arr[64 * m + 32] = 0.0;
+                    small |= 1u << m;
+                    const unsigned bit = 1u << l;
+                    if (fabs(g) <= kEps * (fabs(dlnew) + fabs(dnext))) small |= bit; else small &= ~bit;
                 }
-                dnext = dnew;
-                if (valid) rec[pos] = make_double2(c, s);
-                ++pos;
             }
-            if (broke) {
-                for (; i >= l; --i) { if (valid) rec[pos] = make_double2(1.0, 0.0); ++pos; }
-                // rare path: rebuild the flags from scratch
-                small = 1u << (d - 1);
-                for (int k = 0; k < d - 1; ++k) {
-                    const double dd = fabs(sd[k * 32 + lane]) + fabs(sd[(k + 1) * 32 + lane]);
-                    if (fabs(se[k * 32 + lane]) <= kEps * dd) small |= 1u << k;
-                }
-                continue;
-            }
-            const double dlnew = sd[l * 32 + lane] - pp;
-            sd[l * 32 + lane] = dlnew;
-            se[l * 32 + lane] = g;
-            se[m * 32 + lane] = 0.0;
-            small |= 1u << m;
-            {
-                const unsigned bit = 1u << l;
-                if (fabs(g) <= kEps * (fabs(dlnew) + fabs(dnext))) small |= bit; else small &= ~bit;
-            }
+            ++round;
         }
+        if (lane == 0) a.nrounds[batch] = overflow ? 0 : round;
         if (valid) {
-            hdr[ns] = kTerm;
             if (overflow) {
-                hdr[0] = kTerm;
                 const int slot = atomicAdd(a.overflow_count, 1);
                 a.overflow_list[slot] = (int)p;
             }
-            for (int m = 0; m < d; ++m) a.ev[p * d + m] = sd[m * 32 + lane];
+            for (int m = 0; m < d; ++m) a.ev[p * d + m] = arr[64 * m];
         }
         __syncwarp();
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// K_B: warp-per-point.  D = compile-time padded dimension (rows/cols >= d stay identity).
+// K_B helpers
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double fast_rcp(double x) {
     double r;
@@ -173,7 +208,6 @@ __device__ __forceinline__ double fast_rcp(double x) {
     r = fma(fma(-x, r, 1.0), r, r);
     return r;
 }
-
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gmem_src) : "memory");
@@ -182,272 +216,405 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int kRing = 4;                   // sweeps of rotation records in flight per warp
+#ifdef QTET_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[8];
+#define PHASE_MARK(idx) do { const long long _t = clock64(); if (lane == 0) atomicAdd(&g_phase_cycles[idx], (unsigned long long)(_t - _t0)); _t0 = _t; } while (0)
+#define PHASE_START() long long _t0 = clock64()
+#else
+#define PHASE_MARK(idx) do {} while (0)
+#define PHASE_START() do {} while (0)
+#endif
 
-template <int D>
-__global__ void __launch_bounds__(kWarpsB * 32, 5) apply_kernel(SplitArgs a, int smem_per_warp_doubles) {
+// Sum over the G lanes of a point (G a power of two, groups are aligned).
+template <int G>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int D, int G>
+struct BLayout {
+    static constexpr int R = (D + G - 1) / G;          // rows of V per lane
+    static constexpr int RZ = (D + G - 1) / G;         // eigen-indices owned per lane
+    static constexpr int PPW = 32 / G;                 // points per warp
+    static constexpr int NPL = D - 1;                  // planes
+    static constexpr int ROWS_PER_COPY = 32 / PPW;     // stream rows moved by one warp-wide cp.async
+    static constexpr int NCOPY = (NPL + ROWS_PER_COPY - 1) / ROWS_PER_COPY;
+    static constexpr int DH = (D + 1) / 2;             // half of the eigen-indices (a-reduction in two halves)
+    static constexpr int NP = D * (D - 1) / 2;         // index pairs i < j
+    // shared memory per warp, in doubles
+    static constexpr int RING = kRing * NPL * PPW * 2;                 // double2 [kRing][NPL][PPW]
+    static constexpr int HDR = kMaxRounds * PPW / 2;                   // unsigned [kMaxRounds][PPW]
+    static constexpr int ZB = 2 * PPW * D * 2;                         // double2 [2][PPW][D]
+    static constexpr int LV = 8 * PPW * D;                             // double [8][PPW][D]
+    static constexpr int PART = PPW * G * DH * 2;                      // double2 [PPW][G][DH]
+    static constexpr int SM_S = PPW * (D + NP);                        // double [PPW][D + NP]
+    static constexpr int GRAD = ((LV + (PART > SM_S ? PART : SM_S)) + 1) & ~1;
+    static constexpr int ROT = RING + HDR;
+    static constexpr int PHASED = (ROT > GRAD ? ROT : GRAD);
+    static constexpr int PER_WARP = ((PHASED + ZB + PPW * D) + 1) & ~1;    // + c vector [PPW][D]
+};
+
+// ------------------------------------------------------------------------------------------------
+// K_B: G lanes per point, R rows per lane in registers.
+// ------------------------------------------------------------------------------------------------
+template <int D, int G, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) apply_kernel(SplitArgs a) {
+    using L = BLayout<D, G>;
+    constexpr int R = L::R, RZ = L::RZ, PPW = L::PPW, NPL = L::NPL, NP = L::NP;
     extern __shared__ double sm[];
     const ProblemView& pv = a.pv;
     const int d = pv.d, f = pv.f, T = pv.T;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* base = sm + (size_t)warp * smem_per_warp_doubles;
-    double2* rbuf = reinterpret_cast<double2*>(base);          // [kRing][32]  staged rotations by plane index
-    double2* zbuf = rbuf + kRing * 32;                          // [2][32]  z_i = c_i f_i^k                                  // [2][32]  z_i = c_i f_i^k
-    double* lanev = reinterpret_cast<double*>(zbuf + 64);       // [8][32]  per-eigen-index vectors for the gradient
-    unsigned* hbuf = reinterpret_cast<unsigned*>(lanev + 8 * 32);   // [kMaxSweeps + kRing] sweep headers
-    double* U = lanev + 8 * 32 + (kMaxSweeps + 8) / 2;                                 // union: p[T][LDU] | V^T staging [D][LDU] | S packed
-    constexpr int LDU = D | 1;                                  // odd row pitch: conflict-free column reads
+    const int g = lane / G, q = lane % G;                       // point slot in the warp, lane within the point
+    double* base = sm + (size_t)warp * L::PER_WARP;
+    // rotation phase
+    double2* ring = reinterpret_cast<double2*>(base);                        // [kRing][NPL][PPW]
+    unsigned* hb = reinterpret_cast<unsigned*>(base + L::RING);              // [kMaxRounds][PPW]
+    // gradient phase (aliases the rotation phase)
+    double* lv = base;                                                       // [8][PPW][D]
+    double2* part = reinterpret_cast<double2*>(base + L::LV);                // [PPW][G][DH]
+    double* sbuf = base + L::LV;                                             // [PPW][D + NP]
+    // always live
+    double2* zbuf = reinterpret_cast<double2*>(base + L::PHASED);            // [2][PPW][D]
+    double* cbuf = base + L::PHASED + L::ZB;                                 // [PPW][D]
 
-    const double wsite = (lane < d) ? pv.occ[lane * f + a.site] : 0.0;
     const double dt = (T > 1) ? pv.tgrid[1] : 0.0;
-
-    for (long long p = (long long)blockIdx.x * kWarpsB + warp; p < a.n; p += (long long)gridDim.x * kWarpsB) {
-        const unsigned* hdr = a.hdr + p * kMaxSweeps;
-        unsigned H0 = hdr[lane], H1 = hdr[32 + lane], H2 = hdr[64 + lane], H3 = hdr[96 + lane];
-        const double2* rec = a.stream + p * a.cap;
-        double v[D];
+    double wsite[R];
 #pragma unroll
-        for (int k = 0; k < D; ++k) v[k] = (k == lane) ? 1.0 : 0.0;
+    for (int k = 0; k < R; ++k) {
+        const int row = q * R + k;
+        wsite[k] = (row < d) ? pv.occ[row * f + a.site] : 0.0;
+    }
+    // roles for moving stream rows into the ring: (row cj0 + ROWS_PER_COPY * t, point cg)
+    const int cg = lane % PPW, cj0 = lane / PPW;
 
-        // ---- replay the rotation stream.  Records travel global -> shared with cp.async, kRing-1 sweeps
-        // ahead of their use (each lane copies one record of a sweep straight to its plane slot), so the
-        // HBM/L2 latency of the stream is off the critical path.  Sweep headers (l | m<<8 | pos<<16) are
-        // staged in shared memory once per point.
-        hbuf[lane] = H0; hbuf[32 + lane] = H1; hbuf[64 + lane] = H2; hbuf[96 + lane] = H3;
-        if (lane < kRing) hbuf[kMaxSweeps + lane] = kTerm;
+    const long long nbatch = (a.n + 31) / 32;
+    const long long ntask = nbatch * G;                          // G warps' worth of work per batch
+    for (long long task = (long long)blockIdx.x * WARPS + warp; task < ntask; task += (long long)gridDim.x * WARPS) {
+        PHASE_START();
+        const long long batch = task / G;
+        const int sub = (int)(task - batch * G);
+        const int blane = sub * PPW + g;                         // my point's lane in the K_A batch
+        const long long p = batch * 32 + blane;
+        const bool valid = p < a.n;
+        const int nr = a.nrounds[batch];
+        const double2* rec = a.stream + (size_t)batch * a.capit * 32 + sub * PPW;
+        const unsigned* hdr = a.hdr + (size_t)batch * kMaxRounds * 32 + sub * PPW;
+
+        double v[R][D];
+#pragma unroll
+        for (int k = 0; k < R; ++k)
+#pragma unroll
+            for (int i = 0; i < D; ++i) v[k][i] = (i == q * R + k) ? 1.0 : 0.0;
+
+        // ---- stage the round headers of my PPW points: hb[r][pt]
         __syncwarp();
-        auto issue = [&](int s) {
-            const unsigned hh = hbuf[s];
-            if (hh != kTerm) {
-                const int li = hh & 0xff, mi = (hh >> 8) & 0xff, pi = hh >> 16;
-                if (lane < mi - li) cp_async16(rbuf + (s % kRing) * 32 + (mi - 1 - lane), rec + pi + lane);
+        for (int idx = lane; idx < nr * PPW; idx += 32) hb[idx] = hdr[(idx / PPW) * 32 + (idx % PPW)];
+        __syncwarp();
+
+        // ---- replay the rounds.  Records travel global -> shared with cp.async, kRing-1 rounds ahead of
+        // their use, straight into their plane slot; cells outside a point's window [l, m) hold identity.
+        auto issue = [&](int r) {
+            if (r < nr) {
+                const unsigned hh = hb[r * PPW + cg];
+                const int li = hh & 0xff, mi = (hh >> 8) & 0xff, it0 = hh >> 16;
+                const bool idle = (li == 0xff);
+                double2* slot = ring + (r % kRing) * NPL * PPW;
+#pragma unroll
+                for (int t = 0; t < L::NCOPY; ++t) {
+                    const int j = cj0 + t * L::ROWS_PER_COPY;      // plane index for the fill, stream row for the copy
+                    if (j < NPL) {
+                        if (idle || j < li || j >= mi) slot[j * PPW + cg] = make_double2(1.0, 0.0);
+                        if (!idle && j < mi - li)
+                            cp_async16(slot + (mi - 1 - j) * PPW + cg, rec + (size_t)(it0 + j) * 32 + cg);
+                    }
+                }
             }
             cp_async_commit();
         };
 #pragma unroll
-        for (int s = 0; s < kRing - 1; ++s) issue(s);
-        unsigned h = hbuf[0];
-        for (int s = 0; h != kTerm; ++s) {
-            const int l = h & 0xff, m = (h >> 8) & 0xff;
+        for (int r = 0; r < kRing - 1; ++r) issue(r);
+        for (int r = 0; r < nr; ++r) {
             __syncwarp();                                   // everyone is done with the slot about to be refilled
-            issue(s + kRing - 1);
-            h = hbuf[s + 1];
-            cp_async_wait<kRing - 1>();                     // this lane's records of sweep s have landed
-            double2* rb = rbuf + (s % kRing) * 32;
-            // identity outside the window [l, m): above an interior split, and below l down to the group edge
-            if (lane < D - 1 && (lane >= m || lane < l)) rb[lane] = make_double2(1.0, 0.0);
+            issue(r + kRing - 1);
+            const unsigned h = hb[r * PPW + g];
+            const int myl = h & 0xff;
+            const int lmin = __reduce_min_sync(0xffffffffu, myl);          // idle points carry l = 255
+            cp_async_wait<kRing - 1>();                     // this lane's copies of round r have landed
             __syncwarp();
-            // Planes D-2 .. l, top-down, in groups of four with ONE warp-uniform exit test per group (QL
-            // deflates from the top, so the window is almost always the suffix [l, d-2]).  Inside a group the
-            // code is branch-free: the four (c, s) loads are issued ahead of the dependent chain and only one
-            // fma per plane sits on that chain:  v[i] <- c x - s y  with  c x  computed off-chain.
+            if (lmin >= NPL) continue;                      // nobody in this warp sweeps in this round
+            const double2* rb = ring + (r % kRing) * NPL * PPW + g;
+            // Planes D-2 .. lmin, top-down, in groups of four with ONE warp-uniform exit test per group.
+            // Inside a group the code is branch-free: (c, s) of four planes are fetched ahead of the R
+            // independent dependency chains, and only one fma per row and plane sits on a chain:
+            //   v[i] <- c x - s y  with  c x  computed off-chain.
 #pragma unroll
             for (int i0 = D - 2; i0 >= 0; i0 -= 4) {
-                if (i0 < l) break;
+                if (i0 < lmin) break;
                 double2 cs[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) cs[k] = rb[(i0 - k >= 0) ? (i0 - k) : 0];
+                for (int k4 = 0; k4 < 4; ++k4) cs[k4] = rb[((i0 - k4 >= 0) ? (i0 - k4) : 0) * PPW];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int i = i0 - k;
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const int i = i0 - k4;
                     if (i >= 0) {
-                        const double x = v[i], y = v[i + 1];
-                        const double t1 = cs[k].x * x, t2 = cs[k].y * x;
-                        v[i] = fma(-cs[k].y, y, t1);
-                        v[i + 1] = fma(cs[k].x, y, t2);
+#pragma unroll
+                        for (int k = 0; k < R; ++k) {
+                            const double x = v[k][i], y = v[k][i + 1];
+                            const double t1 = cs[k4].x * x, t2 = cs[k4].y * x;
+                            v[k][i] = fma(-cs[k4].y, y, t1);
+                            v[k][i + 1] = fma(cs[k4].x, y, t2);
+                        }
                     }
                 }
             }
         }
         cp_async_wait<0>();
+        PHASE_MARK(0);
 
-        // ---- c = V[0,:], eigenvalues, unit phase step w = exp(-i e dt)
+        // ---- c = V[0,:] (row 0 lives in lane q = 0, k = 0), eigenvalues and unit phase steps of my indices
         __syncwarp();
-        if (lane == 0) {
+        if (q == 0) {
 #pragma unroll
-            for (int k = 0; k < D; ++k) lanev[k] = v[k];
+            for (int i = 0; i < D; ++i) cbuf[g * D + i] = v[0][i];
         }
         __syncwarp();
-        const double ci = (lane < D) ? lanev[lane] : 0.0;
-        const double ei = (lane < d) ? a.ev[p * d + lane] : 0.0;
-        double wre, wim;
-        {
-            const double th = ei * dt;
-            const double lo = fma(ei, dt, -th);             // exact product tail
+        double ei[RZ], ci[RZ], wre[RZ], wim[RZ], zr[RZ], zi[RZ];
+#pragma unroll
+        for (int t = 0; t < RZ; ++t) {
+            const int i = q + t * G;
+            ci[t] = (i < D) ? cbuf[g * D + i] : 0.0;
+            ei[t] = (i < d && valid) ? a.ev[p * d + i] : 0.0;
+            const double th = ei[t] * dt;
+            const double lo = fma(ei[t], dt, -th);          // exact product tail
             double sn, cs;
             sincos(th, &sn, &cs);
-            // exp(-i (th + lo)) = (cs - i sn)(1 - i lo)
-            wre = fma(-sn, lo, cs);
-            wim = -fma(cs, lo, sn);
+            wre[t] = fma(-sn, lo, cs);                      // exp(-i (th + lo)) = (cs - i sn)(1 - i lo)
+            wim[t] = -fma(cs, lo, sn);
+            zr[t] = ci[t]; zi[t] = 0.0;
         }
-        __syncwarp();
+        PHASE_MARK(1);
 
-        // ---- time evolution: p_j(k) = n_site(j) |psi_j(t_k)|^2 staged as U[k][j]
-        double zr = ci, zi = 0.0;
-        for (int k = 0; k < T; ++k) {
-            double2* zb = zbuf + (k & 1) * 32;
-            zb[lane] = make_double2(zr, zi);
-            __syncwarp();
-            double ar4[4] = {0.0, 0.0, 0.0, 0.0}, ai4[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-            for (int i = 0; i < D; ++i) {
-                const double2 z0 = zb[i];
-                ar4[i & 3] = fma(v[i], z0.x, ar4[i & 3]);
-                ai4[i & 3] = fma(v[i], z0.y, ai4[i & 3]);
-            }
-            const double pr = (ar4[0] + ar4[1]) + (ar4[2] + ar4[3]), pi = (ai4[0] + ai4[1]) + (ai4[2] + ai4[3]);
-            if (lane < D) U[k * LDU + lane] = wsite * fma(pr, pr, pi * pi);
-            const double nr = fma(zr, wre, -(zi * wim));
-            zi = fma(zr, wim, zi * wre);
-            zr = nr;
-        }
-        __syncwarp();
-        // lane k sums step k over rows; arg-max / arg-min with the first index winning ties
+        // ---- time evolution: n(t_k) = sum_rows n_site |psi_row(t_k)|^2, running arg-max / arg-min
         int kbest = 0;
         double vbest = 0.0;
-        for (int k0 = 0; k0 < T; k0 += 32) {
-            const int k = k0 + lane;
-            double nk = 0.0;
-            if (k < T) {
+        for (int k = 0; k < T; ++k) {
+            double2* zb = zbuf + ((k & 1) * PPW + g) * D;
 #pragma unroll
-                for (int j = 0; j < D; ++j) nk += U[k * LDU + j];
-                if (a.trace) a.trace[p * T + k] = nk;
+            for (int t = 0; t < RZ; ++t) {
+                const int i = q + t * G;
+                if (i < D) zb[i] = make_double2(zr[t], zi[t]);
             }
-            double key = (k < T) ? (a.acceptor ? nk : -nk) : -1.0e300;
-            int kk = k;
+            __syncwarp();
+            double pr[R][2], pi[R][2];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ok = __shfl_xor_sync(0xffffffffu, key, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, kk, o);
-                if (ok > key || (ok == key && oi < kk)) { key = ok; kk = oi; }
+            for (int kk = 0; kk < R; ++kk) { pr[kk][0] = pr[kk][1] = 0.0; pi[kk][0] = pi[kk][1] = 0.0; }
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                const double2 z = zb[i];
+#pragma unroll
+                for (int kk = 0; kk < R; ++kk) {
+                    pr[kk][i & 1] = fma(v[kk][i], z.x, pr[kk][i & 1]);
+                    pi[kk][i & 1] = fma(v[kk][i], z.y, pi[kk][i & 1]);
+                }
             }
-            if (k0 == 0 || key > vbest) { vbest = key; kbest = kk; }
+            double part_n = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < R; ++kk) {
+                const double re = pr[kk][0] + pr[kk][1], im = pi[kk][0] + pi[kk][1];
+                part_n = fma(wsite[kk], fma(re, re, im * im), part_n);
+            }
+            const double nk = group_sum<G>(part_n);
+            if (a.trace && valid && q == (k % G)) a.trace[p * T + k] = nk;
+            const double key = a.acceptor ? nk : -nk;
+            if (k == 0 || key > vbest) { vbest = key; kbest = k; }          // first extremum wins ties
+#pragma unroll
+            for (int t = 0; t < RZ; ++t) {
+                const double nr_ = fma(zr[t], wre[t], -(zi[t] * wim[t]));
+                zi[t] = fma(zr[t], wim[t], zi[t] * wre[t]);
+                zr[t] = nr_;
+            }
         }
-        if (lane == 0) {
+        if (q == 0 && valid) {
             if (a.loss) a.loss[p] = a.acceptor ? ((double)pv.N - vbest) : -vbest;
             if (a.tstar) a.tstar[p] = kbest;
         }
-        __syncwarp();
-        if (a.grad == nullptr) continue;
+        PHASE_MARK(2);
+        if (a.grad == nullptr) { __syncwarp(); continue; }
 
-        // ---- gradient at t* = t_kbest: f_i = w_i^kbest by binary powering
-        double fr = 1.0, fi = 0.0;
-        {
-            double br = wre, bi = wim;
+        // ---- gradient at t* = t_kbest: f_i = w_i^kbest by binary powering (my eigen-indices)
+        const double ts = pv.tgrid[kbest];
+        double fr[RZ], fi[RZ];
+#pragma unroll
+        for (int t = 0; t < RZ; ++t) {
+            double xr = 1.0, xi = 0.0, br = wre[t], bi = wim[t];
             for (int e = kbest; e > 0; e >>= 1) {
-                if (e & 1) { const double t = fma(fr, br, -(fi * bi)); fi = fma(fr, bi, fi * br); fr = t; }
+                if (e & 1) { const double tt = fma(xr, br, -(xi * bi)); xi = fma(xr, bi, xi * br); xr = tt; }
                 const double t2 = fma(br, br, -(bi * bi)); bi = 2.0 * br * bi; br = t2;
             }
+            fr[t] = xr; fi[t] = xi;
         }
-        const double ts = pv.tgrid[kbest];
+        __syncwarp();
         {
-            double2* zb = zbuf;
-            zb[lane] = make_double2(ci * fr, ci * fi);
+            double2* zb = zbuf + g * D;
+#pragma unroll
+            for (int t = 0; t < RZ; ++t) {
+                const int i = q + t * G;
+                if (i < D) zb[i] = make_double2(ci[t] * fr[t], ci[t] * fi[t]);
+            }
         }
         __syncwarp();
-        double pr = 0.0, pi = 0.0;
+        double wcr[R], wci[R];                               // n_site(row) conj(psi_row(t*))
+        {
+            const double2* zb = zbuf + g * D;
+            double pr[R], pi[R];
 #pragma unroll
-        for (int i = 0; i < D; ++i) { const double2 z = zbuf[i]; pr = fma(v[i], z.x, pr); pi = fma(v[i], z.y, pi); }
-        // w conj(psi) per row, then a = V^T (w conj psi) through a transposed copy of V in shared memory
-        double2* wc = zbuf + 32;
-        wc[lane] = make_double2(wsite * pr, -wsite * pi);
-        if (lane < D) {
+            for (int kk = 0; kk < R; ++kk) { pr[kk] = 0.0; pi[kk] = 0.0; }
 #pragma unroll
-            for (int i = 0; i < D; ++i) U[lane * LDU + i] = v[i];
+            for (int i = 0; i < D; ++i) {
+                const double2 z = zb[i];
+#pragma unroll
+                for (int kk = 0; kk < R; ++kk) { pr[kk] = fma(v[kk][i], z.x, pr[kk]); pi[kk] = fma(v[kk][i], z.y, pi[kk]); }
+            }
+#pragma unroll
+            for (int kk = 0; kk < R; ++kk) { wcr[kk] = wsite[kk] * pr[kk]; wci[kk] = -wsite[kk] * pi[kk]; }
+        }
+        // a_i = sum_rows V[row][i] wc_row : per-lane partial sums over my rows, combined through shared
+        // memory in two halves of i; the owner of eigen-index i adds the G partials.
+        double ar[RZ], ai[RZ];
+#pragma unroll
+        for (int t = 0; t < RZ; ++t) { ar[t] = 0.0; ai[t] = 0.0; }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            __syncwarp();
+#pragma unroll
+            for (int ii = 0; ii < L::DH; ++ii) {
+                const int i = half * L::DH + ii;
+                if (i < D) {
+                    double sr = 0.0, si = 0.0;
+#pragma unroll
+                    for (int kk = 0; kk < R; ++kk) { sr = fma(v[kk][i], wcr[kk], sr); si = fma(v[kk][i], wci[kk], si); }
+                    part[(g * G + q) * L::DH + ii] = make_double2(sr, si);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < RZ; ++t) {
+                const int i = q + t * G;
+                const int ii = i - half * L::DH;
+                if (i < D && ii >= 0 && ii < L::DH) {
+#pragma unroll
+                    for (int qq = 0; qq < G; ++qq) { const double2 x = part[(g * G + qq) * L::DH + ii]; ar[t] += x.x; ai[t] += x.y; }
+                }
+            }
         }
         __syncwarp();
-        double ar = 0.0, ai = 0.0;
-        const int lcol = (lane < D) ? lane : 0;
+        // per-eigen-index vectors of my point: e, c, f, a, b = a f ; diagonal of the kernel K_ii = c_i t* Im(b_i)
+        double* lvp = lv + g * D;
+        double* sp = sbuf + g * (D + NP);
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-            const double vt = U[j * LDU + lcol];          // V[j][lane]
-            const double2 w = wc[j];
-            ar = fma(vt, w.x, ar); ai = fma(vt, w.y, ai);
+        for (int t = 0; t < RZ; ++t) {
+            const int i = q + t * G;
+            if (i < D) {
+                const double bre = fma(ar[t], fr[t], -(ai[t] * fi[t])), bim = fma(ar[t], fi[t], ai[t] * fr[t]);
+                lvp[0 * PPW * D + i] = ei[t]; lvp[1 * PPW * D + i] = ci[t];
+                lvp[2 * PPW * D + i] = fr[t]; lvp[3 * PPW * D + i] = fi[t];
+                lvp[4 * PPW * D + i] = ar[t]; lvp[5 * PPW * D + i] = ai[t];
+                lvp[6 * PPW * D + i] = bre; lvp[7 * PPW * D + i] = bim;
+                sp[i] = ci[t] * ts * bim;
+            }
         }
         __syncwarp();
-        // per-eigen-index vectors: e, c, f, a, b = a f
-        const double bre = fma(ar, fr, -(ai * fi)), bim = fma(ar, fi, ai * fr);
-        lanev[0 * 32 + lane] = ei; lanev[1 * 32 + lane] = ci;
-        lanev[2 * 32 + lane] = fr; lanev[3 * 32 + lane] = fi;
-        lanev[4 * 32 + lane] = ar; lanev[5 * 32 + lane] = ai;
-        lanev[6 * 32 + lane] = bre; lanev[7 * 32 + lane] = bim;
-        // S packed: diagonal K_ii at U[i], pairs (i<j) at U[32 + q]
-        U[lane] = ci * ts * bim;
-        __syncwarp();
-        constexpr int NP = D * (D - 1) / 2;
-        for (int q = lane; q < NP; q += 32) {
-            const unsigned ij = a.pair_tab[q];
+        for (int qq = q; qq < NP; qq += G) {
+            const unsigned ij = a.pair_tab[qq];
             const int i = ij & 0xff, j = ij >> 8;
-            const double e_i = lanev[i], e_j = lanev[j];
-            const double c_i = lanev[32 + i], c_j = lanev[32 + j];
+            const double e_i = lvp[i], e_j = lvp[j];
+            const double c_i = lvp[PPW * D + i], c_j = lvp[PPW * D + j];
             const double dl = e_i - e_j;
             double sij;
             if (fabs(dl * ts) < 1e-2) {
-                // Phi_ij = ts * f_j * (exp(-i x) - 1)/x ; S = Re[(a_i c_j + a_j c_i) Phi_ij]
+                // Phi_ij = ts f_j (exp(-i x) - 1)/x ; S = Re[(a_i c_j + a_j c_i) Phi_ij]
                 double gr, gi;
                 expm1_over_x(dl * ts, gr, gi);
-                const double fjr = lanev[64 + j], fji = lanev[96 + j];
+                const double fjr = lvp[2 * PPW * D + j], fji = lvp[3 * PPW * D + j];
                 const double phr = ts * (fjr * gr - fji * gi), phi = ts * (fjr * gi + fji * gr);
-                const double mr = lanev[128 + i] * c_j + lanev[128 + j] * c_i;
-                const double mi = lanev[160 + i] * c_j + lanev[160 + j] * c_i;
+                const double mr = lvp[4 * PPW * D + i] * c_j + lvp[4 * PPW * D + j] * c_i;
+                const double mi = lvp[5 * PPW * D + i] * c_j + lvp[5 * PPW * D + j] * c_i;
                 sij = mr * phr - mi * phi;
             } else {
                 const double rinv = fast_rcp(dl);
                 // K_ij = c_j R (br_i - ar_i fr_j + ai_i fi_j) ; K_ji = -c_i R (br_j - ar_j fr_i + ai_j fi_i)
-                const double kij = c_j * (lanev[192 + i] - lanev[128 + i] * lanev[64 + j] + lanev[160 + i] * lanev[96 + j]);
-                const double kji = c_i * (lanev[192 + j] - lanev[128 + j] * lanev[64 + i] + lanev[160 + j] * lanev[96 + i]);
+                const double kij = c_j * (lvp[6 * PPW * D + i] - lvp[4 * PPW * D + i] * lvp[2 * PPW * D + j] + lvp[5 * PPW * D + i] * lvp[3 * PPW * D + j]);
+                const double kji = c_i * (lvp[6 * PPW * D + j] - lvp[4 * PPW * D + j] * lvp[2 * PPW * D + i] + lvp[5 * PPW * D + j] * lvp[3 * PPW * D + i]);
                 sij = rinv * (kij - kji);
             }
-            U[32 + q] = sij;
+            sp[D + qq] = sij;
         }
         __syncwarp();
-        double G = 0.0;
+        PHASE_MARK(3);
+        double Gm[R];
+#pragma unroll
+        for (int kk = 0; kk < R; ++kk) Gm[kk] = 0.0;
         {
-            int q = 0;
+            int qq = 0;
 #pragma unroll
             for (int i = 0; i < D; ++i) {
-                double acc = U[i] * v[i];
+                const double kd = sp[i];
+                double acc[R];
 #pragma unroll
-                for (int j = i + 1; j < D; ++j) { acc = fma(U[32 + q], v[j], acc); ++q; }
-                G = fma(v[i], acc, G);
+                for (int kk = 0; kk < R; ++kk) acc[kk] = kd * v[kk][i];
+#pragma unroll
+                for (int j = i + 1; j < D; ++j) {
+                    const double sv = sp[D + qq];
+                    ++qq;
+#pragma unroll
+                    for (int kk = 0; kk < R; ++kk) acc[kk] = fma(sv, v[kk][j], acc[kk]);
+                }
+#pragma unroll
+                for (int kk = 0; kk < R; ++kk) Gm[kk] = fma(v[kk][i], acc[kk], Gm[kk]);
             }
         }
-        G *= 2.0;
+        PHASE_MARK(4);
         for (int k = 0; k < f; ++k) {
-            const double qk = (lane < d) ? pv.quad[lane * f + k] : 0.0;
-            const double sres = warp_sum(qk * G);
-            if (lane == 0) a.grad[p * f + k] = a.acceptor ? -sres : sres;
+            double s = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < R; ++kk) {
+                const int row = q * R + kk;
+                const double qk = (row < d) ? pv.quad[row * f + k] : 0.0;
+                s = fma(qk, 2.0 * Gm[kk], s);
+            }
+            s = group_sum<G>(s);
+            if (q == 0 && valid) a.grad[p * f + k] = a.acceptor ? -s : s;
         }
         __syncwarp();
+        PHASE_MARK(5);
     }
 }
 
-template <int D>
+template <int D, int G, int WARPS, int MINB>
 int launch_apply(const SplitArgs& a, int sms, cudaStream_t st) {
-    const int T = a.pv.T;
-    const int urows = (T > D) ? T : D;
-    int udoubles = urows * (D | 1);
-    const int need_s = 32 + D * (D - 1) / 2;
-    if (need_s > udoubles) udoubles = need_s;
-    udoubles = (udoubles + 1) & ~1;
-    const int per_warp = 2 * kRing * 32 + 128 + 8 * 32 + (kMaxSweeps + 8) / 2 + udoubles;
-    const size_t smem = (size_t)per_warp * kWarpsB * sizeof(double);
-    QTET_CUDA(cudaFuncSetAttribute(apply_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    QTET_CUDA(cudaFuncSetAttribute(apply_kernel<D>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    using L = BLayout<D, G>;
+    const size_t smem = (size_t)L::PER_WARP * WARPS * sizeof(double);
+    auto kern = apply_kernel<D, G, WARPS, MINB>;
+    QTET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QTET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int per_sm = 0;
-    QTET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, apply_kernel<D>, kWarpsB * 32, smem));
+    QTET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
     if (per_sm < 1) per_sm = 1;
     long long grid = (long long)sms * per_sm;
-    const long long need = (a.n + kWarpsB - 1) / kWarpsB;
+    const long long ntask = ((a.n + 31) / 32) * G;
+    const long long need = (ntask + WARPS - 1) / WARPS;
     if (grid > need) grid = need;
-    apply_kernel<D><<<(unsigned)grid, kWarpsB * 32, smem, st>>>(a, per_warp);
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(a);
     count_launch();
     QTET_CUDA(cudaGetLastError());
     return QTET_OK;
 }
 
 int padded_dim(int d) {
-    const int sizes[] = {4, 6, 8, 12, 16, 21, 24, 32};
+    const int sizes[] = {4, 8, 16, 21, 24, 32};
     for (int s : sizes) if (d <= s) return s;
     return -1;
 }
@@ -456,7 +623,7 @@ int padded_dim(int d) {
 
 struct SplitWorkspace {
     int device = 0, sms = 0;
-    int cap = 0, D = 0;
+    int capit = 0, D = 0;
     long long chunk = 0;
     char* blob = nullptr;            // two chunk buffers (double-buffered between K_A and K_B)
     size_t blob_bytes = 0;
@@ -466,8 +633,16 @@ struct SplitWorkspace {
     cudaEvent_t ev_fork = nullptr, ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr};
 };
 
+#ifdef QTET_PHASE_TIMING
+extern "C" void qtet_debug_phase_cycles(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)); }
+}
+#endif
+
 bool split_eligible(const ProblemView& pv) {
-    return pv.tridiag && pv.d >= 2 && pv.d <= 32 && pv.T <= 64 && pv.f <= 8;
+    return pv.tridiag && pv.d >= 2 && pv.d <= 32 && pv.f <= 8;
 }
 
 void split_workspace_free(SplitWorkspace* ws) {
@@ -488,9 +663,6 @@ void split_workspace_free(SplitWorkspace* ws) {
 int launch_generic_list(const ProblemView& pv, const double* chis, const int* list, const int* count, long long max_count,
                         int site, double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st);
 
-template <int D>
-static int apply_dispatch(const SplitArgs& a, int sms, cudaStream_t st) { return launch_apply<D>(a, sms, st); }
-
 int launch_split(const ProblemView& pv, SplitWorkspace** wsp, const double* chis, int64_t B, int site,
                  double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st) {
     if (B <= 0) return QTET_OK;
@@ -503,7 +675,7 @@ int launch_split(const ProblemView& pv, SplitWorkspace** wsp, const double* chis
         QTET_CUDA(cudaGetDevice(&ws->device));
         QTET_CUDA(cudaDeviceGetAttribute(&ws->sms, cudaDevAttrMultiProcessorCount, ws->device));
         ws->D = padded_dim(d);
-        ws->cap = (3 * d * d) / 2 + 64;
+        ws->capit = 2 * d * d + 64;                       // stream rows per batch (warp iterations)
         std::vector<unsigned short> tab;
         for (int i = 0; i < ws->D; ++i)
             for (int j = i + 1; j < ws->D; ++j) tab.push_back((unsigned short)(i | (j << 8)));
@@ -518,18 +690,20 @@ int launch_split(const ProblemView& pv, SplitWorkspace** wsp, const double* chis
             QTET_CUDA(cudaEventCreateWithFlags(&ws->ev_b[i], cudaEventDisableTiming));
         }
     }
-    // per-point workspace: rotation stream + sweep headers + eigenvalues + overflow slot
-    const size_t per_point = (size_t)ws->cap * sizeof(double2) + kMaxSweeps * sizeof(unsigned) + (size_t)d * 8 + 4;
-    // chunking: two buffers in flight; aim for >= 8 chunks on big batches so that K_A(c+1) overlaps K_B(c),
-    // but keep chunks large enough to fill the machine several times over
-    long long chunk = (long long)((size_t)4 << 30) / (long long)per_point;      // <= 4 GiB per buffer
-    long long want = (B + 3) / 4;
-    if (want < 131072) want = 131072;
-    if (chunk > want) chunk = want;
-    chunk = ((chunk + 4095) / 4096) * 4096;
-    if (chunk > B) chunk = ((B + 31) / 32) * 32;
-    const size_t o_hdr = (size_t)chunk * ws->cap * sizeof(double2);
-    const size_t o_ev = o_hdr + (size_t)chunk * kMaxSweeps * sizeof(unsigned);
+    // per-batch workspace: rotation stream + round headers + round count; per point: eigenvalues + overflow slot
+    const size_t per_batch = (size_t)ws->capit * 32 * sizeof(double2) + (size_t)kMaxRounds * 32 * sizeof(unsigned) + 4 +
+                             32 * ((size_t)d * 8 + 4);
+    // chunking: two buffers in flight so that K_A(c+1) overlaps K_B(c); chunks large enough to fill the machine
+    long long chunk_b = (long long)((size_t)2 << 30) / (long long)per_batch;    // <= 2 GiB per buffer
+    long long want_b = ((B + 31) / 32 + 3) / 4;
+    if (want_b < 2048) want_b = 2048;
+    if (chunk_b > want_b) chunk_b = want_b;
+    const long long all_b = (B + 31) / 32;
+    if (chunk_b > all_b) chunk_b = all_b;
+    const long long chunk = chunk_b * 32;
+    const size_t o_hdr = (size_t)chunk_b * ws->capit * 32 * sizeof(double2);
+    const size_t o_nr = o_hdr + (size_t)chunk_b * kMaxRounds * 32 * sizeof(unsigned);
+    const size_t o_ev = o_nr + (((size_t)chunk_b * 4 + 255) / 256) * 256;
     const size_t o_list = o_ev + (((size_t)chunk * d * 8 + 255) / 256) * 256;
     const size_t buf_bytes = ((o_list + (size_t)chunk * 4 + 255) / 256) * 256;
     const size_t total = 2 * buf_bytes;
@@ -543,7 +717,7 @@ int launch_split(const ProblemView& pv, SplitWorkspace** wsp, const double* chis
     ws->chunk = chunk;
 
     SplitArgs a;
-    a.pv = pv; a.site = site; a.acceptor = (site == pv.f - 1) ? 1 : 0; a.cap = ws->cap;
+    a.pv = pv; a.site = site; a.acceptor = (site == pv.f - 1) ? 1 : 0; a.capit = ws->capit;
     a.pair_tab = ws->pair_tab;
 
     const size_t smemA = (size_t)kWarpsA * 2 * d * 32 * sizeof(double);
@@ -561,7 +735,7 @@ int launch_split(const ProblemView& pv, SplitWorkspace** wsp, const double* chis
         const int buf = c & 1;
         char* base = ws->blob + (size_t)buf * buf_bytes;
         const long long n = (B - lo < chunk) ? (B - lo) : chunk;
-        a.stream = (double2*)base; a.hdr = (unsigned*)(base + o_hdr);
+        a.stream = (double2*)base; a.hdr = (unsigned*)(base + o_hdr); a.nrounds = (int*)(base + o_nr);
         a.ev = (double*)(base + o_ev); a.overflow_list = (int*)(base + o_list);
         a.overflow_count = ws->overflow_count + buf;
         a.chis = chis + lo * pv.f; a.n = n;
@@ -583,14 +757,12 @@ int launch_split(const ProblemView& pv, SplitWorkspace** wsp, const double* chis
         QTET_CUDA(cudaStreamWaitEvent(st, ws->ev_a[buf], 0));
         int rc;
         switch (ws->D) {
-            case 4: rc = apply_dispatch<4>(a, ws->sms, st); break;
-            case 6: rc = apply_dispatch<6>(a, ws->sms, st); break;
-            case 8: rc = apply_dispatch<8>(a, ws->sms, st); break;
-            case 12: rc = apply_dispatch<12>(a, ws->sms, st); break;
-            case 16: rc = apply_dispatch<16>(a, ws->sms, st); break;
-            case 21: rc = apply_dispatch<21>(a, ws->sms, st); break;
-            case 24: rc = apply_dispatch<24>(a, ws->sms, st); break;
-            default: rc = apply_dispatch<32>(a, ws->sms, st); break;
+            case 4: rc = launch_apply<4, 4, 4, 4>(a, ws->sms, st); break;
+            case 8: rc = launch_apply<8, 8, 4, 4>(a, ws->sms, st); break;
+            case 16: rc = launch_apply<16, 8, 2, 6>(a, ws->sms, st); break;
+            case 21: rc = launch_apply<21, 8, 2, 4>(a, ws->sms, st); break;
+            case 24: rc = launch_apply<24, 8, 2, 4>(a, ws->sms, st); break;
+            default: rc = launch_apply<32, 16, 2, 4>(a, ws->sms, st); break;
         }
         if (rc) return rc;
         // overflowed points (if any) are recomputed by the fused generic kernel
