@@ -217,7 +217,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 #ifdef QTET_PHASE_TIMING
-__device__ unsigned long long g_phase_cycles[8];
+__device__ unsigned long long g_phase_cycles[16];
 #define PHASE_MARK(idx) do { const long long _t = clock64(); if (lane == 0) atomicAdd(&g_phase_cycles[idx], (unsigned long long)(_t - _t0)); _t0 = _t; } while (0)
 #define PHASE_START() long long _t0 = clock64()
 #else
@@ -280,6 +280,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) apply_kernel(SplitArgs a) {
     double2* zbuf = reinterpret_cast<double2*>(base + L::PHASED);            // [2][PPW][D]
     double* cbuf = base + L::PHASED + L::ZB;                                 // [PPW][D]
 
+    __shared__ unsigned short s_pair[NP > 0 ? NP : 1];
+    for (int i = threadIdx.x; i < NP; i += blockDim.x) s_pair[i] = a.pair_tab[i];
+    __syncthreads();
     const double dt = (T > 1) ? pv.tgrid[1] : 0.0;
     double wsite[R];
 #pragma unroll
@@ -337,13 +340,21 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) apply_kernel(SplitArgs a) {
 #pragma unroll
         for (int r = 0; r < kRing - 1; ++r) issue(r);
         for (int r = 0; r < nr; ++r) {
+#ifndef QTET_EXP_NOSYNC1
             __syncwarp();                                   // everyone is done with the slot about to be refilled
+#endif
+#ifndef QTET_EXP_NOISSUE
             issue(r + kRing - 1);
+#endif
             const unsigned h = hb[r * PPW + g];
             const int myl = h & 0xff;
             const int lmin = __reduce_min_sync(0xffffffffu, myl);          // idle points carry l = 255
+#ifndef QTET_EXP_NOISSUE
             cp_async_wait<kRing - 1>();                     // this lane's copies of round r have landed
+#endif
+#ifndef QTET_EXP_NOSYNC2
             __syncwarp();
+#endif
             if (lmin >= NPL) continue;                      // nobody in this warp sweeps in this round
             const double2* rb = ring + (r % kRing) * NPL * PPW + g;
             // Planes D-2 .. lmin, top-down, in groups of four with ONE warp-uniform exit test per group.
@@ -352,7 +363,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) apply_kernel(SplitArgs a) {
             //   v[i] <- c x - s y  with  c x  computed off-chain.
 #pragma unroll
             for (int i0 = D - 2; i0 >= 0; i0 -= 4) {
+#ifndef QTET_EXP_NOEXIT
                 if (i0 < lmin) break;
+#endif
                 double2 cs[4];
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) cs[k4] = rb[((i0 - k4 >= 0) ? (i0 - k4) : 0) * PPW];
@@ -456,6 +469,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) apply_kernel(SplitArgs a) {
             }
             fr[t] = xr; fi[t] = xi;
         }
+        PHASE_MARK(6);
         __syncwarp();
         {
             double2* zb = zbuf + g * D;
@@ -481,6 +495,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) apply_kernel(SplitArgs a) {
 #pragma unroll
             for (int kk = 0; kk < R; ++kk) { wcr[kk] = wsite[kk] * pr[kk]; wci[kk] = -wsite[kk] * pi[kk]; }
         }
+        PHASE_MARK(7);
         // a_i = sum_rows V[row][i] wc_row : per-lane partial sums over my rows, combined through shared
         // memory in two halves of i; the owner of eigen-index i adds the G partials.
         double ar[RZ], ai[RZ];
@@ -511,6 +526,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) apply_kernel(SplitArgs a) {
             }
         }
         __syncwarp();
+        PHASE_MARK(8);
         // per-eigen-index vectors of my point: e, c, f, a, b = a f ; diagonal of the kernel K_ii = c_i t* Im(b_i)
         double* lvp = lv + g * D;
         double* sp = sbuf + g * (D + NP);
@@ -527,30 +543,50 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) apply_kernel(SplitArgs a) {
             }
         }
         __syncwarp();
-        for (int qq = q; qq < NP; qq += G) {
-            const unsigned ij = a.pair_tab[qq];
-            const int i = ij & 0xff, j = ij >> 8;
-            const double e_i = lvp[i], e_j = lvp[j];
-            const double c_i = lvp[PPW * D + i], c_j = lvp[PPW * D + j];
-            const double dl = e_i - e_j;
-            double sij;
-            if (fabs(dl * ts) < 1e-2) {
-                // Phi_ij = ts f_j (exp(-i x) - 1)/x ; S = Re[(a_i c_j + a_j c_i) Phi_ij]
-                double gr, gi;
-                expm1_over_x(dl * ts, gr, gi);
-                const double fjr = lvp[2 * PPW * D + j], fji = lvp[3 * PPW * D + j];
-                const double phr = ts * (fjr * gr - fji * gi), phi = ts * (fjr * gi + fji * gr);
-                const double mr = lvp[4 * PPW * D + i] * c_j + lvp[4 * PPW * D + j] * c_i;
-                const double mi = lvp[5 * PPW * D + i] * c_j + lvp[5 * PPW * D + j] * c_i;
-                sij = mr * phr - mi * phi;
-            } else {
-                const double rinv = fast_rcp(dl);
-                // K_ij = c_j R (br_i - ar_i fr_j + ai_i fi_j) ; K_ji = -c_i R (br_j - ar_j fr_i + ai_j fi_i)
-                const double kij = c_j * (lvp[6 * PPW * D + i] - lvp[4 * PPW * D + i] * lvp[2 * PPW * D + j] + lvp[5 * PPW * D + i] * lvp[3 * PPW * D + j]);
-                const double kji = c_i * (lvp[6 * PPW * D + j] - lvp[4 * PPW * D + j] * lvp[2 * PPW * D + i] + lvp[5 * PPW * D + j] * lvp[3 * PPW * D + i]);
-                sij = rinv * (kij - kji);
+        PHASE_MARK(9);
+        // S_ij = K_ij + K_ji for i < j; pairs dealt round-robin to the G lanes of the point, four pairs in
+        // flight per lane (independent load -> reciprocal -> product chains), rare near-degenerate pairs fixed up
+        // afterwards.
+        for (int q0 = q; q0 < NP; q0 += 4 * G) {
+            int pi_[4], pj_[4];
+            double dl[4], kd[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int qq = q0 + u * G;
+                const unsigned ij = s_pair[(qq < NP) ? qq : 0];
+                pi_[u] = ij & 0xff; pj_[u] = ij >> 8;
             }
-            sp[D + qq] = sij;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = pi_[u], j = pj_[u];
+                dl[u] = lvp[i] - lvp[j];
+                // K_ij = c_j R (br_i - ar_i fr_j + ai_i fi_j) ; K_ji = -c_i R (br_j - ar_j fr_i + ai_j fi_i)
+                const double kij = lvp[PPW * D + j] * (lvp[6 * PPW * D + i] - lvp[4 * PPW * D + i] * lvp[2 * PPW * D + j] + lvp[5 * PPW * D + i] * lvp[3 * PPW * D + j]);
+                const double kji = lvp[PPW * D + i] * (lvp[6 * PPW * D + j] - lvp[4 * PPW * D + j] * lvp[2 * PPW * D + i] + lvp[5 * PPW * D + j] * lvp[3 * PPW * D + i]);
+                kd[u] = kij - kji;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) kd[u] *= fast_rcp(dl[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int qq = q0 + u * G;
+                if (qq < NP) {
+                    double sij = kd[u];
+                    if (fabs(dl[u] * ts) < 1e-2) {
+                        // near-degenerate: Phi_ij = ts f_j (exp(-i x) - 1)/x ; S = Re[(a_i c_j + a_j c_i) Phi_ij]
+                        const int i = pi_[u], j = pj_[u];
+                        double gr, gi;
+                        expm1_over_x(dl[u] * ts, gr, gi);
+                        const double fjr = lvp[2 * PPW * D + j], fji = lvp[3 * PPW * D + j];
+                        const double phr = ts * (fjr * gr - fji * gi), phi = ts * (fjr * gi + fji * gr);
+                        const double c_i = lvp[PPW * D + i], c_j = lvp[PPW * D + j];
+                        const double mr = lvp[4 * PPW * D + i] * c_j + lvp[4 * PPW * D + j] * c_i;
+                        const double mi = lvp[5 * PPW * D + i] * c_j + lvp[5 * PPW * D + j] * c_i;
+                        sij = mr * phr - mi * phi;
+                    }
+                    sp[D + qq] = sij;
+                }
+            }
         }
         __syncwarp();
         PHASE_MARK(3);
@@ -636,8 +672,8 @@ struct SplitWorkspace {
 #ifdef QTET_PHASE_TIMING
 extern "C" void qtet_debug_phase_cycles(unsigned long long* out, int reset) {
     cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 8);
-    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)); }
+    cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)); }
 }
 #endif
 

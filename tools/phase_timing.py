@@ -26,13 +26,13 @@ x = torch.from_numpy(pts).cuda()
 for _ in range(2):
     prob.loss_grad(x)
 torch.cuda.synchronize()
-out = (ctypes.c_ulonglong * 8)()
+out = (ctypes.c_ulonglong * 16)()
 _native.lib.qtet_debug_phase_cycles(out, 1)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); prob.loss_grad(x); e1.record(); torch.cuda.synchronize()
 _native.lib.qtet_debug_phase_cycles(out, 0)
-names = ["rotations", "c/eig/phase setup", "evolution", "time reduce+loss", "gradient (to S,G)", "grad reduce+store"]
-tot = sum(out[i] for i in range(6))
+names = ["0 rotations", "1 c/eig/phase setup", "2 evolution+loss", "3 S pairs", "4 G = row S row", "5 grad reduce+store", "6 f=w^k powering", "7 psi(t*)", "8 a reduction", "9 records"]
+tot = sum(out[i] for i in range(len(names)))
 print(f"B={B} N={N} total step {e0.elapsed_time(e1):.3f} ms ; warp-cycles per point:")
 for i, n in enumerate(names):
     print(f"  {n:22s} {out[i]/B:10.1f} cycles/pt  {100*out[i]/tot:5.1f}%")
