@@ -30,7 +30,7 @@ constexpr double kEps = 1.1102230246251565e-16;
 constexpr int kMaxRounds = 128;            // header rows per batch
 constexpr int kWarpsA = 4;                 // warps per CTA, scalar kernel
 constexpr int kRing = 4;                   // rounds of rotation records in flight per warp (K_B)
-constexpr unsigned kIdle = 0xffffu;        // l = m = 0xff : lane takes no part in the round
+constexpr unsigned kIdle = 63u;            // l field of a lane that takes no part in the round
 
 struct SplitArgs {
     ProblemView pv;
@@ -39,7 +39,7 @@ struct SplitArgs {
     int site, acceptor;
     int capit;                // stream rows (warp iterations) per batch
     double2* stream;          // [nb][capit][32]
-    unsigned* hdr;            // [nb][kMaxRounds][32]   l | m << 8 | it0 << 16
+    unsigned* hdr;            // [nb][kMaxRounds][32]   l (63 = idle) | mtop << 6 | lbot << 12 | it0 << 18
     int* nrounds;             // [nb]
     double* ev;               // [n, d]  eigenvalues (shifted by the mean of the diagonal)
     int* overflow_list;       // [n]
@@ -51,134 +51,190 @@ struct SplitArgs {
 __device__ __forceinline__ unsigned lowmask(int l) { return (l >= 32) ? 0xffffffffu : ((1u << l) - 1u); }
 
 // ------------------------------------------------------------------------------------------------
-// K_A: thread-per-point scalar QL in warp-synchronous rounds.  diag/off live in shared memory as
-// [2k + {0,1}][lane] (bank = lane: lanes may sit at different k without conflicts).
+// K_A: thread-per-point scalar QL.  diag/off live in shared memory as [2k + {0,1}][lane] (bank = lane:
+// lanes may sit at different k without conflicts).
+//
+//   pass 1  plain implicit-shift QL (Wilkinson shifts), eigenvalues only, nothing recorded;
+//   pass 2  the tridiagonal is rebuilt and swept again in warp-synchronous ROUNDS, this time recorded.
+//           The first sweep at every index l uses the eigenvalue pass 1 left at that index as a PERFECT
+//           shift (one sweep deflates it: ~d sweeps and ~d^2/2 rotations instead of ~1.7 d and ~0.9 d^2);
+//           if rounding spoils a deflation the loop simply continues with Wilkinson shifts, so the result
+//           never depends on pass 1 being right.
+//
+// A round covers the planes mtop-1 .. lbot (warp-uniform: the union of the lanes' windows); stream row
+// it0 + (mtop-1-i) holds, for every lane, the rotation of plane i or the identity if the lane does not
+// touch that plane in this round.  Rows are written by all 32 lanes: fully coalesced 512 B stores.
 // ------------------------------------------------------------------------------------------------
+struct QlLane {
+    double* arr;       // diag k at arr[64 k], off k at arr[64 k + 32]
+    int d;
+    __device__ __forceinline__ double& dg(int k) const { return arr[64 * k]; }
+    __device__ __forceinline__ double& of(int k) const { return arr[64 * k + 32]; }
+    __device__ __forceinline__ unsigned scan_small() const {
+        unsigned small = 1u << (d - 1);
+        for (int k = 0; k < d - 1; ++k) {
+            const double dd = fabs(dg(k)) + fabs(dg(k + 1));
+            if (fabs(of(k)) <= kEps * dd) small |= 1u << k;
+        }
+        return small;
+    }
+    __device__ __forceinline__ double wilkinson_g(int l, int m) const {
+        const double dl = dg(l), el = of(l);
+        const double gg = (dg(l + 1) - dl) / (2.0 * el);
+        const double rr = sqrt(fma(gg, gg, 1.0));
+        return dg(m) - dl + el / (gg + copysign(rr, gg));
+    }
+};
+
 __global__ void __launch_bounds__(kWarpsA * 32) ql_scalar_kernel(SplitArgs a) {
     extern __shared__ double sm[];
     const ProblemView& pv = a.pv;
     const int d = pv.d, f = pv.f;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* arr = sm + (size_t)warp * 2 * d * 32 + lane;     // diag k at arr[64 k], off k at arr[64 k + 32]
+    QlLane t;
+    t.arr = sm + (size_t)warp * 2 * d * 32 + lane;
+    t.d = d;
     const long long nbatch = (a.n + 31) / 32;
     const unsigned below_top = lowmask(d - 1);
     for (long long batch = (long long)blockIdx.x * kWarpsA + warp; batch < nbatch; batch += (long long)gridDim.x * kWarpsA) {
         const long long p = batch * 32 + lane;
         const bool valid = p < a.n;
         const long long pc = valid ? p : a.n - 1;
-        // ---- H build (HamiltonianLoss.py:131-134) + global-phase shift by the mean of the diagonal
         double hchi[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) hchi[k] = (k < f) ? 0.5 * a.chis[pc * f + k] : 0.0;
+        double lam[32];                                    // eigenvalue pass 1 left at each index (local memory)
         double mean = 0.0;
-        for (int m = 0; m < d; ++m) {
-            double acc = 0.0;
+        for (int pass = 0; pass < 2; ++pass) {
+            // ---- H build (HamiltonianLoss.py:131-134) + global-phase shift by the mean of the diagonal
+            double sum = 0.0;
+            for (int m = 0; m < d; ++m) {
+                double acc = 0.0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if (k < f) {
-                    const double n = pv.occ[m * f + k];
-                    acc = acc + (pv.omegas[k] * n + hchi[k] * (n * n));
+                for (int k = 0; k < 8; ++k) {
+                    if (k < f) {
+                        const double n = pv.occ[m * f + k];
+                        acc = acc + (pv.omegas[k] * n + hchi[k] * (n * n));
+                    }
                 }
+                t.dg(m) = acc;
+                t.of(m) = (m < d - 1) ? pv.offd[m] : 0.0;
+                sum += acc;
             }
-            arr[64 * m] = acc;
-            arr[64 * m + 32] = (m < d - 1) ? pv.offd[m] : 0.0;
-            mean += acc;
+            if (pass == 0) mean = sum / (double)d;
+            for (int m = 0; m < d; ++m) t.dg(m) -= mean;
+            if (pass == 1) break;
+            // ---- pass 1: eigenvalues only
+            unsigned small = t.scan_small();
+            int l = 0, iter = 0;
+            while (true) {
+                const unsigned alive = (~small) & below_top & ~lowmask(l);
+                if (alive == 0u) break;
+                const int lnew = __ffs(alive) - 1;
+                if (lnew != l) iter = 0;
+                l = lnew;
+                const int m = l + __ffs(small >> l) - 1;
+                if (++iter > 60) break;                    // give up quietly: pass 2 does not rely on pass 1
+                double g = t.wilkinson_g(l, m);
+                double s = 1.0, c = 1.0, pp = 0.0, dnext = 0.0;
+                bool broke = false;
+                for (int i = m - 1; i >= l; --i) {
+                    const double ei = t.of(i);
+                    const double fo = s * ei, bo = c * ei;
+                    const double r2 = fma(fo, fo, g * g);
+                    if (r2 == 0.0) { t.of(i + 1) = 0.0; t.dg(i + 1) -= pp; t.of(m) = 0.0; broke = true; break; }
+                    const double rinv = rsqrt(r2);
+                    const double r = r2 * rinv;
+                    s = fo * rinv; c = g * rinv;
+                    g = t.dg(i + 1) - pp;
+                    const double rr = fma(t.dg(i) - g, s, 2.0 * c * bo);
+                    pp = s * rr;
+                    const double dnew = g + pp;
+                    t.dg(i + 1) = dnew;
+                    g = fma(c, rr, -bo);
+                    if (i + 1 < m) {
+                        t.of(i + 1) = r;
+                        const unsigned bit = 1u << (i + 1);
+                        if (r <= kEps * (fabs(dnew) + fabs(dnext))) small |= bit; else small &= ~bit;
+                    }
+                    dnext = dnew;
+                }
+                if (broke) { small = t.scan_small(); continue; }
+                const double dlnew = t.dg(l) - pp;
+                t.dg(l) = dlnew; t.of(l) = g; t.of(m) = 0.0;
+                small |= 1u << m;
+                const unsigned bit = 1u << l;
+                if (fabs(g) <= kEps * (fabs(dlnew) + fabs(dnext))) small |= bit; else small &= ~bit;
+            }
+            for (int m = 0; m < d; ++m) lam[m] = t.dg(m);
         }
-        mean /= (double)d;
-        for (int m = 0; m < d; ++m) arr[64 * m] -= mean;
 
+        // ---- pass 2: recorded rounds
         double2* rec = a.stream + (size_t)batch * a.capit * 32 + lane;
         unsigned* hdr = a.hdr + (size_t)batch * kMaxRounds * 32 + lane;
-        // bit k of `small`: off[k] is negligible against its diagonal neighbours (bit d-1: sentinel).
-        // Initialised by one scan, then kept current inside the sweeps (only swept entries change).
-        unsigned small = 1u << (d - 1);
-        for (int k = 0; k < d - 1; ++k) {
-            const double dd = fabs(arr[64 * k]) + fabs(arr[64 * k + 64]);
-            if (fabs(arr[64 * k + 32]) <= kEps * dd) small |= 1u << k;
-        }
-        int it = 0, round = 0, l = 0, iter = 0;
+        unsigned small = t.scan_small();
+        int it = 0, round = 0, l = 0, iter = 0, tried = -1;
         bool overflow = false;
         while (true) {
-            // first index >= l whose off-diagonal is still alive; none -> this lane is finished
             const unsigned alive = (~small) & below_top & ~lowmask(l);
             const bool done = (alive == 0u);
             const int lnew = done ? d : (__ffs(alive) - 1);
             if (lnew != l) iter = 0;
             l = lnew;
             if (__all_sync(0xffffffffu, done)) break;
-            const int m = done ? l : (l + __ffs(small >> l) - 1);      // first negligible off-diagonal above l
+            const int m = done ? 0 : (l + __ffs(small >> l) - 1);       // first negligible off-diagonal above l
             ++iter;
-            const int cnt = done ? 0 : (m - l);
-            const int maxcnt = __reduce_max_sync(0xffffffffu, cnt);
-            if (__any_sync(0xffffffffu, !done && iter > 60) || round >= kMaxRounds - 1 || it + maxcnt > a.capit) {
+            const int mtop = __reduce_max_sync(0xffffffffu, m);
+            const int lbot = __reduce_min_sync(0xffffffffu, done ? 63 : l);
+            const int nrows = mtop - lbot;
+            if (__any_sync(0xffffffffu, !done && iter > 60) || round >= kMaxRounds - 1 || it + nrows > a.capit) {
                 overflow = true;
                 break;
             }
-            hdr[round * 32] = done ? (kIdle | ((unsigned)it << 16)) : ((unsigned)l | ((unsigned)m << 8) | ((unsigned)it << 16));
+            hdr[round * 32] = (unsigned)(done ? 63 : l) | ((unsigned)mtop << 6) | ((unsigned)lbot << 12) | ((unsigned)it << 18);
             double g = 0.0, s = 1.0, c = 1.0, pp = 0.0, dnext = 0.0;
-            if (!done) {                                   // Wilkinson shift from the leading 2x2 of the block
-                const double dl = arr[64 * l], el = arr[64 * l + 32];
-                const double gg = (arr[64 * l + 64] - dl) / (2.0 * el);
-                const double rr = sqrt(fma(gg, gg, 1.0));
-                g = arr[64 * m] - dl + el / (gg + copysign(rr, gg));
+            if (!done) {
+                if (tried != l) { tried = l; g = t.dg(m) - lam[l]; }    // perfect shift, first sweep at this index
+                else g = t.wilkinson_g(l, m);
             }
             bool broke = false;
-            int i = done ? 0 : (m - 1);
-            // software-pipelined operands of the first plane: e[i], d[i], d[i+1]
-            double ei = arr[64 * i + 32], di = arr[64 * i], di1 = arr[64 * i + 64];
-            for (int j = 0; j < maxcnt; ++j) {
-                if (j < cnt && !broke) {
-                    // operands of the next plane, fetched before this plane's stores
-                    const int inx = (i > l) ? (i - 1) : i;
-                    const double ei_n = arr[64 * inx + 32];
-                    const double di_n = arr[64 * inx];
+            double2* row = rec + (size_t)it * 32;
+            for (int i = mtop - 1; i >= lbot; --i, row += 32) {
+                double2 out = make_double2(1.0, 0.0);
+                if (!done && !broke && i < m && i >= l) {
+                    const double ei = t.of(i);
                     const double fo = s * ei, bo = c * ei;
                     const double r2 = fma(fo, fo, g * g);
                     if (r2 == 0.0) {                       // underflow recovery: the rest of the sweep is identity
-                        arr[64 * (i + 1) + 32] = 0.0;
-                        arr[64 * (i + 1)] = di1 - pp;
-                        arr[64 * m + 32] = 0.0;
+                        t.of(i + 1) = 0.0; t.dg(i + 1) -= pp; t.of(m) = 0.0;
                         broke = true;
-                        if (valid) rec[(size_t)(it + j) * 32] = make_double2(1.0, 0.0);
                     } else {
                         const double rinv = rsqrt(r2);
                         const double r = r2 * rinv;
-                        s = fo * rinv;
-                        c = g * rinv;
-                        g = di1 - pp;
-                        const double rr = fma(di - g, s, 2.0 * c * bo);
+                        s = fo * rinv; c = g * rinv;
+                        g = t.dg(i + 1) - pp;
+                        const double rr = fma(t.dg(i) - g, s, 2.0 * c * bo);
                         pp = s * rr;
                         const double dnew = g + pp;
-                        arr[64 * (i + 1)] = dnew;
+                        t.dg(i + 1) = dnew;
                         g = fma(c, rr, -bo);
                         if (i + 1 < m) {                   // off[i+1] = r is final: refresh its flag
-                            arr[64 * (i + 1) + 32] = r;
+                            t.of(i + 1) = r;
                             const unsigned bit = 1u << (i + 1);
                             if (r <= kEps * (fabs(dnew) + fabs(dnext))) small |= bit; else small &= ~bit;
                         }
                         dnext = dnew;
-                        if (valid) rec[(size_t)(it + j) * 32] = make_double2(c, s);
-                        // the next plane's d[i+1] is this plane's (untouched) d[i]
-                        di1 = di; di = di_n; ei = ei_n;
-                        --i;
+                        out = make_double2(c, s);
                     }
-                } else if (j < cnt) {
-                    if (valid) rec[(size_t)(it + j) * 32] = make_double2(1.0, 0.0);
                 }
+                *row = out;                                // all 32 lanes: one coalesced 512 B row
             }
-            it += maxcnt;
+            it += nrows;
             if (!done) {
-                if (broke) {                               // rare path: rebuild the flags from scratch
-                    small = 1u << (d - 1);
-                    for (int k = 0; k < d - 1; ++k) {
-                        const double dd = fabs(arr[64 * k]) + fabs(arr[64 * k + 64]);
-                        if (fabs(arr[64 * k + 32]) <= kEps * dd) small |= 1u << k;
-                    }
-                } else {
-                    const double dlnew = arr[64 * l] - pp;
-                    arr[64 * l] = dlnew;
-                    arr[64 * l + 32] = g;
-                    arr[64 * m + 32] = 0.0;
+                if (broke) small = t.scan_small();         // rare path: rebuild the flags from scratch
+                else {
+                    const double dlnew = t.dg(l) - pp;
+                    t.dg(l) = dlnew; t.of(l) = g; t.of(m) = 0.0;
                     small |= 1u << m;
                     const unsigned bit = 1u << l;
                     if (fabs(g) <= kEps * (fabs(dlnew) + fabs(dnext))) small |= bit; else small &= ~bit;
@@ -192,7 +248,7 @@ __global__ void __launch_bounds__(kWarpsA * 32) ql_scalar_kernel(SplitArgs a) {
                 const int slot = atomicAdd(a.overflow_count, 1);
                 a.overflow_list[slot] = (int)p;
             }
-            for (int m = 0; m < d; ++m) a.ev[p * d + m] = arr[64 * m];
+            for (int m = 0; m < d; ++m) a.ev[p * d + m] = t.dg(m);
         }
         __syncwarp();
     }
@@ -317,22 +373,19 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) apply_kernel(SplitArgs a) {
         for (int idx = lane; idx < nr * PPW; idx += 32) hb[idx] = hdr[(idx / PPW) * 32 + (idx % PPW)];
         __syncwarp();
 
-        // ---- replay the rounds.  Records travel global -> shared with cp.async, kRing-1 rounds ahead of
-        // their use, straight into their plane slot; cells outside a point's window [l, m) hold identity.
+        // ---- replay the rounds.  A round's rows (one per plane, top-down from mtop-1) travel global -> shared
+        // with cp.async kRing-1 rounds ahead of their use; the cells of my PPW points are 16 B x PPW contiguous
+        // in every row and already hold the identity where a point does not touch a plane.
         auto issue = [&](int r) {
             if (r < nr) {
-                const unsigned hh = hb[r * PPW + cg];
-                const int li = hh & 0xff, mi = (hh >> 8) & 0xff, it0 = hh >> 16;
-                const bool idle = (li == 0xff);
+                const unsigned hh = hb[r * PPW];                       // uniform fields of the round
+                const int mtop_i = (hh >> 6) & 63, lbot_i = (hh >> 12) & 63, it0 = hh >> 18;
+                const int nrows = mtop_i - lbot_i;
                 double2* slot = ring + (r % kRing) * NPL * PPW;
 #pragma unroll
                 for (int t = 0; t < L::NCOPY; ++t) {
-                    const int j = cj0 + t * L::ROWS_PER_COPY;      // plane index for the fill, stream row for the copy
-                    if (j < NPL) {
-                        if (idle || j < li || j >= mi) slot[j * PPW + cg] = make_double2(1.0, 0.0);
-                        if (!idle && j < mi - li)
-                            cp_async16(slot + (mi - 1 - j) * PPW + cg, rec + (size_t)(it0 + j) * 32 + cg);
-                    }
+                    const int j = cj0 + t * L::ROWS_PER_COPY;
+                    if (j < nrows) cp_async16(slot + j * PPW + cg, rec + (size_t)(it0 + j) * 32 + cg);
                 }
             }
             cp_async_commit();
@@ -340,35 +393,30 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) apply_kernel(SplitArgs a) {
 #pragma unroll
         for (int r = 0; r < kRing - 1; ++r) issue(r);
         for (int r = 0; r < nr; ++r) {
-#ifndef QTET_EXP_NOSYNC1
             __syncwarp();                                   // everyone is done with the slot about to be refilled
-#endif
-#ifndef QTET_EXP_NOISSUE
             issue(r + kRing - 1);
-#endif
             const unsigned h = hb[r * PPW + g];
-            const int myl = h & 0xff;
-            const int lmin = __reduce_min_sync(0xffffffffu, myl);          // idle points carry l = 255
-#ifndef QTET_EXP_NOISSUE
+            const int mtop = (h >> 6) & 63;
+            const int lcur = __reduce_min_sync(0xffffffffu, (int)(h & 63));   // idle points carry l = 63
             cp_async_wait<kRing - 1>();                     // this lane's copies of round r have landed
-#endif
-#ifndef QTET_EXP_NOSYNC2
             __syncwarp();
-#endif
-            if (lmin >= NPL) continue;                      // nobody in this warp sweeps in this round
-            const double2* rb = ring + (r % kRing) * NPL * PPW + g;
-            // Planes D-2 .. lmin, top-down, in groups of four with ONE warp-uniform exit test per group.
+            if (lcur >= mtop) continue;                     // none of my points sweeps in this round
+            // plane i sits in row mtop-1-i of the slot
+            const double2* rb = ring + (r % kRing) * NPL * PPW + (mtop - 1) * PPW + g;
+            // Planes mtop-1 .. lcur, top-down, in groups of four with ONE warp-uniform exit test per group.
             // Inside a group the code is branch-free: (c, s) of four planes are fetched ahead of the R
             // independent dependency chains, and only one fma per row and plane sits on a chain:
             //   v[i] <- c x - s y  with  c x  computed off-chain.
 #pragma unroll
             for (int i0 = D - 2; i0 >= 0; i0 -= 4) {
-#ifndef QTET_EXP_NOEXIT
-                if (i0 < lmin) break;
-#endif
+                if (i0 < lcur) break;
+                if (i0 - 3 >= mtop) continue;               // whole group above the swept range (padding / split)
                 double2 cs[4];
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) cs[k4] = rb[((i0 - k4 >= 0) ? (i0 - k4) : 0) * PPW];
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const int i = i0 - k4;
+                    cs[k4] = (i >= 0 && i < mtop && i >= lcur) ? rb[-i * PPW] : make_double2(1.0, 0.0);
+                }
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {
                     const int i = i0 - k4;
