@@ -223,6 +223,7 @@ def main():
         step()
     barrier()
 
+    prob.profile(True)                       # CUDA events around every kernel the library launches
     sampler = ClockSampler(local)
     sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -236,6 +237,8 @@ def main():
     barrier()
     launches = _native.launch_count() - launches0
     clocks = sampler.stop()
+    kern = prob.profile_read()               # {kernel: (ms_sum, launches, points)} over the timed region
+    prob.profile(False)
     ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(ms))
     if world > 1:
@@ -278,7 +281,24 @@ def main():
         except Exception:
             peak = None
         per_gpu_rate = B * args.steps / (total_ms * 1e-3)
-        achieved = per_gpu_rate * F / 1e12
+        # dominant kernel: algorithmic flops of the points one launch processes / its average launch duration
+        kms = {k: v for k, v in kern.items() if v[1] > 0}
+        dom = max(kms, key=lambda k: kms[k][0]) if kms else None
+        kernels = {k: {"launches": v[1], "ms_per_launch": v[0] / v[1], "points_per_launch": v[2] / v[1],
+                       "share_of_kernel_time": v[0] / sum(x[0] for x in kms.values())} for k, v in kms.items()}
+        if dom:
+            dms, dn, dpts = kms[dom]
+            achieved = (dpts / dn) * F / (dms / dn * 1e-3) / 1e12
+        else:
+            achieved = per_gpu_rate * F / 1e12
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+                tj = json.load(fh)
+            if dom in tj and tj[dom].get("workload") == args.workload:
+                traffic = tj[dom]["dram_bytes_per_point"] * (kms[dom][2] / kms[dom][1])
+        except Exception:
+            pass
         peaks = {}
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -287,8 +307,9 @@ def main():
             pass
         hbm_bytes = (8 * f) + 8 * (1 + f) + 4
         roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": (achieved / peak) if peak else None, "traffic": None,
-                    "flops_per_eval": F,
+                    "frac": (achieved / peak) if peak else None, "traffic": traffic,
+                    "flops_per_eval": F, "kernel": dom, "kernels": kernels,
+                    "whole_step": {"achieved": per_gpu_rate * F / 1e12, "frac": (per_gpu_rate * F / 1e12 / peak) if peak else None},
                     "peak_source": "FP64 DFMA micro-benchmark run inside this bench (MEASURED_PEAKS.json has no FP64 figure)",
                     "kernel_path": path_name,
                     "hbm": {"algorithmic_bytes_per_eval": hbm_bytes, "achieved_GBps": per_gpu_rate * hbm_bytes / 1e9,

@@ -118,6 +118,13 @@ int qtet_argmin(const double* values_dev, int64_t B, double* min_dev, int64_t* i
  * roofline denominator because MEASURED_PEAKS.json carries no FP64 figure. */
 int qtet_fp64_peak(int device, double seconds_budget, double* tflops_out);
 
+/* Per-kernel timing (CUDA events on the launching streams).  kind 0: scalar QL kernel, 1: rotation-replay /
+ * evolution / gradient kernel (the dominant one), 2: fused generic kernel.  enable(on=1) clears the records;
+ * read() synchronises the device and returns, per kind, the summed duration [ms], the number of launches and
+ * the number of parameter points they processed (arrays of 3). */
+int qtet_profile_enable(qtet_problem* p, int on);
+int qtet_profile_read(qtet_problem* p, double* ms_sum, int64_t* launches, int64_t* points);
+
 /* Number of kernel launches this library has issued in the calling process so far. */
 int64_t qtet_launch_count(void);
 

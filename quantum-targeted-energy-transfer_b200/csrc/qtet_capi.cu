@@ -48,8 +48,8 @@ int ensure_scratch(qtet_problem* p, size_t bytes) {
 int loss_grad_dispatch(qtet_problem* p, const double* chis, int64_t B, int site, double* loss,
                        double* grad, int32_t* tstar, double* trace, cudaStream_t st) {
     if (p->path == QTET_PATH_SPLIT)
-        return launch_split(p->view, &p->split_ws, chis, B, site, loss, grad, tstar, trace, st);
-    return launch_generic(p->view, chis, B, site, loss, grad, tstar, trace, st);
+        return launch_split(p->view, &p->split_ws, chis, B, site, loss, grad, tstar, trace, st, p->prof.on ? &p->prof : nullptr);
+    return launch_generic(p->view, chis, B, site, loss, grad, tstar, trace, st, p->prof.on ? &p->prof : nullptr);
 }
 
 }  // namespace qtet
@@ -161,6 +161,7 @@ void qtet_problem_destroy(qtet_problem* p) {
     if (p->dev_blob) cudaFree(p->dev_blob);
     if (p->scratch) cudaFree(p->scratch);
     split_workspace_free(p->split_ws);
+    p->prof.clear();
     delete p;
 }
 
@@ -265,6 +266,31 @@ int qtet_hamiltonian_host(qtet_problem* p, const double* chis_host, double* H_ho
 int qtet_argmin(const double* values_dev, int64_t B, double* min_dev, int64_t* idx_dev, void* stream) {
     if (B <= 0 || !values_dev || !min_dev || !idx_dev) { set_error("bad argument"); return QTET_EINVAL; }
     return launch_argmin(values_dev, B, min_dev, idx_dev, (cudaStream_t)stream);
+}
+
+int qtet_profile_enable(qtet_problem* p, int on) {
+    if (!p) { set_error("null handle"); return QTET_EINVAL; }
+    QTET_CUDA(cudaSetDevice(p->device));
+    QTET_CUDA(cudaDeviceSynchronize());
+    p->prof.clear();
+    p->prof.on = on != 0;
+    return QTET_OK;
+}
+
+int qtet_profile_read(qtet_problem* p, double* ms_sum, int64_t* launches, int64_t* points) {
+    if (!p || !ms_sum || !launches || !points) { set_error("null argument"); return QTET_EINVAL; }
+    QTET_CUDA(cudaSetDevice(p->device));
+    QTET_CUDA(cudaDeviceSynchronize());
+    for (int k = 0; k < Profiler::kKinds; ++k) {
+        ms_sum[k] = 0.0; launches[k] = 0; points[k] = 0;
+        for (size_t i = 0; i < p->prof.beg[k].size(); ++i) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, p->prof.beg[k][i], p->prof.end[k][i]) == cudaSuccess) {
+                ms_sum[k] += ms; launches[k] += 1; points[k] += p->prof.points[k][i];
+            } else cudaGetLastError();
+        }
+    }
+    return QTET_OK;
 }
 
 int64_t qtet_launch_count(void) { return g_launches.load(); }

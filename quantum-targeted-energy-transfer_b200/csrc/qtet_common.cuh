@@ -32,17 +32,46 @@ void count_launch(int n = 1);
         if (_e != cudaSuccess) return ::qtet::cuda_fail(_e, #call); \
     } while (0)
 
+struct Profiler;
+
 // ---- launchers implemented in the kernel translation units -------------------------------
 int launch_generic(const ProblemView& pv, const double* chis, int64_t B, int site, double* loss,
-                   double* grad, int32_t* tstar, double* trace, cudaStream_t st);
+                   double* grad, int32_t* tstar, double* trace, cudaStream_t st, Profiler* prof = nullptr);
 size_t generic_smem_bytes(int d, int nthreads);
 int generic_threads(int d);
 int launch_build_h(const ProblemView& pv, const double* chis, double* H, cudaStream_t st);
 
+// Optional per-kernel timing with CUDA events on the launching streams (bench.py's roofline figures).
+struct Profiler {
+    static constexpr int kKinds = 3;          // 0: ql_scalar (K_A), 1: apply (K_B), 2: fused generic
+    static constexpr int kMaxPairs = 4096;
+    bool on = false;
+    std::vector<cudaEvent_t> beg[kKinds], end[kKinds];
+    std::vector<long long> points[kKinds];
+    void begin(int kind, long long npoints, cudaStream_t st) {
+        if (!on || (int)beg[kind].size() >= kMaxPairs) return;
+        cudaEvent_t a, b;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        beg[kind].push_back(a); end[kind].push_back(b); points[kind].push_back(npoints);
+        cudaEventRecord(a, st);
+    }
+    void finish(int kind, cudaStream_t st) {
+        if (!on || beg[kind].empty() || (int)beg[kind].size() > kMaxPairs) return;
+        cudaEventRecord(end[kind].back(), st);
+    }
+    void clear() {
+        for (int k = 0; k < kKinds; ++k) {
+            for (auto e : beg[k]) cudaEventDestroy(e);
+            for (auto e : end[k]) cudaEventDestroy(e);
+            beg[k].clear(); end[k].clear(); points[k].clear();
+        }
+    }
+};
+
 struct SplitWorkspace;   // rotation streams etc. (qtet_split.cu)
 bool split_eligible(const ProblemView& pv);
 int launch_split(const ProblemView& pv, SplitWorkspace** ws, const double* chis, int64_t B, int site,
-                 double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st);
+                 double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st, Profiler* prof = nullptr);
 void split_workspace_free(SplitWorkspace* ws);
 
 int launch_argmin(const double* v, int64_t B, double* min_out, int64_t* idx_out, cudaStream_t st);
@@ -60,6 +89,7 @@ struct qtet_problem {
     double* dev_blob = nullptr;             // one allocation holding every constant array
     qtet::ProblemView view{};
     qtet::SplitWorkspace* split_ws = nullptr;
+    qtet::Profiler prof;
     // scratch for *_host convenience calls and the optimiser
     void* scratch = nullptr;
     size_t scratch_bytes = 0;

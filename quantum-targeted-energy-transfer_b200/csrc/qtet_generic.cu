@@ -391,8 +391,11 @@ static int launch_generic_impl(const ProblemView& pv, const double* chis, int64_
 }
 
 int launch_generic(const ProblemView& pv, const double* chis, int64_t B, int site, double* loss,
-                   double* grad, int32_t* tstar, double* trace, cudaStream_t st) {
-    return launch_generic_impl(pv, chis, B, nullptr, nullptr, site, loss, grad, tstar, trace, st);
+                   double* grad, int32_t* tstar, double* trace, cudaStream_t st, Profiler* prof) {
+    if (prof) prof->begin(2, B, st);
+    const int rc = launch_generic_impl(pv, chis, B, nullptr, nullptr, site, loss, grad, tstar, trace, st);
+    if (prof) prof->finish(2, st);
+    return rc;
 }
 
 // Evaluate only the points list[0 .. *count) (count read on the device; at most max_count).

@@ -748,7 +748,7 @@ int launch_generic_list(const ProblemView& pv, const double* chis, const int* li
                         int site, double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st);
 
 int launch_split(const ProblemView& pv, SplitWorkspace** wsp, const double* chis, int64_t B, int site,
-                 double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st) {
+                 double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st, Profiler* prof) {
     if (B <= 0) return QTET_OK;
     if (!split_eligible(pv)) { set_error("split path not eligible for this problem"); return QTET_EUNSUPPORTED; }
     SplitWorkspace* ws = *wsp;
@@ -833,13 +833,16 @@ int launch_split(const ProblemView& pv, SplitWorkspace** wsp, const double* chis
         long long gridA = (long long)ws->sms * per_sm_a;
         const long long needA = ((n + 31) / 32 + kWarpsA - 1) / kWarpsA;
         if (gridA > needA) gridA = needA;
+        if (prof) prof->begin(0, n, ws->aux);
         ql_scalar_kernel<<<(unsigned)gridA, kWarpsA * 32, smemA, ws->aux>>>(a);
         count_launch();
+        if (prof) prof->finish(0, ws->aux);
         QTET_CUDA(cudaGetLastError());
         QTET_CUDA(cudaEventRecord(ws->ev_a[buf], ws->aux));
         // K_B(c) on the caller's stream
         QTET_CUDA(cudaStreamWaitEvent(st, ws->ev_a[buf], 0));
         int rc;
+        if (prof) prof->begin(1, n, st);
         switch (ws->D) {
             case 4: rc = launch_apply<4, 4, 4, 4>(a, ws->sms, st); break;
             case 8: rc = launch_apply<8, 8, 4, 4>(a, ws->sms, st); break;
@@ -848,6 +851,7 @@ int launch_split(const ProblemView& pv, SplitWorkspace** wsp, const double* chis
             case 24: rc = launch_apply<24, 8, 2, 4>(a, ws->sms, st); break;
             default: rc = launch_apply<32, 16, 2, 4>(a, ws->sms, st); break;
         }
+        if (prof) prof->finish(1, st);
         if (rc) return rc;
         // overflowed points (if any) are recomputed by the fused generic kernel
         rc = launch_generic_list(pv, a.chis, a.overflow_list, a.overflow_count, n, site, a.loss, a.grad, a.tstar, a.trace, st);

@@ -47,6 +47,8 @@ def _load():
                                     C.c_double, C.c_double, C.c_int, C.c_double, P, P, P, P, P, P]),
         "qtet_argmin": (C.c_int, [P, C.c_int64, P, P, P]),
         "qtet_fp64_peak": (C.c_int, [C.c_int, C.c_double, D]),
+        "qtet_profile_enable": (C.c_int, [P, C.c_int]),
+        "qtet_profile_read": (C.c_int, [P, D, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
         "qtet_launch_count": (C.c_int64, []),
         "qtet_last_error": (C.c_char_p, []),
         "qtet_version": (C.c_char_p, []),
@@ -62,7 +64,8 @@ lib = _load()
 EXPORTS = ["qtet_problem_create", "qtet_problem_destroy", "qtet_problem_dim", "qtet_problem_states",
            "qtet_problem_time_grid", "qtet_hamiltonian_host", "qtet_set_path", "qtet_get_path",
            "qtet_loss_grad", "qtet_loss_grad_host", "qtet_trace", "qtet_adam_run", "qtet_argmin",
-           "qtet_fp64_peak", "qtet_launch_count", "qtet_last_error", "qtet_version"]
+           "qtet_fp64_peak", "qtet_profile_enable", "qtet_profile_read", "qtet_launch_count", "qtet_last_error",
+           "qtet_version"]
 
 
 def _check(rc: int, what: str) -> int:
@@ -151,6 +154,15 @@ class Problem:
 
     def get_path(self) -> int:
         return int(lib.qtet_get_path(self._h))
+
+    def profile(self, on: bool):
+        _check(lib.qtet_profile_enable(self._h, 1 if on else 0), "qtet_profile_enable")
+
+    def profile_read(self):
+        """{kernel: (ms_sum, launches, points)} for 'ql_scalar', 'apply', 'generic'."""
+        ms = (C.c_double * 3)(); n = (C.c_int64 * 3)(); pts = (C.c_int64 * 3)()
+        _check(lib.qtet_profile_read(self._h, ms, n, pts), "qtet_profile_read")
+        return {k: (ms[i], int(n[i]), int(pts[i])) for i, k in enumerate(("ql_scalar", "apply", "generic"))}
 
     # ---- the hot path --------------------------------------------------------------------
     def _site(self, site) -> int:
