@@ -194,6 +194,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the QTET B200 path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # keep stdout to the single JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION/INFO
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
