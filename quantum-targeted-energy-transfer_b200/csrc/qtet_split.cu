@@ -20,6 +20,8 @@
 // Batches whose stream overflows its slot (pathological convergence) are appended to a list and
 // recomputed by the fused generic kernel; no host synchronisation is involved.  K_A runs one chunk
 // ahead of K_B on an auxiliary stream.
+#include <cstdlib>
+
 #include "qtet_common.cuh"
 
 namespace qtet {
@@ -30,6 +32,7 @@ constexpr double kEps = 1.1102230246251565e-16;
 constexpr int kMaxRounds = 128;            // header rows per batch
 constexpr int kWarpsA = 4;                 // warps per CTA, scalar kernel
 constexpr int kRing = 4;                   // rounds of rotation records in flight per warp (K_B)
+constexpr int kTail = 3;                   // identity rows appended to every round (K_B sweeps planes in groups of 4)
 constexpr unsigned kIdle = 63u;            // l field of a lane that takes no part in the round
 
 struct SplitArgs {
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(kWarpsA * 32) ql_scalar_kernel(SplitArgs a) {
             const int mtop = __reduce_max_sync(0xffffffffu, m);
             const int lbot = __reduce_min_sync(0xffffffffu, done ? 63 : l);
             const int nrows = mtop - lbot;
-            if (__any_sync(0xffffffffu, !done && iter > 60) || round >= kMaxRounds - 1 || it + nrows > a.capit) {
+            if (__any_sync(0xffffffffu, !done && iter > 60) || round >= kMaxRounds - 1 || it + nrows + kTail > a.capit) {
                 overflow = true;
                 break;
             }
@@ -229,7 +232,9 @@ __global__ void __launch_bounds__(kWarpsA * 32) ql_scalar_kernel(SplitArgs a) {
                 }
                 *row = out;                                // all 32 lanes: one coalesced 512 B row
             }
-            it += nrows;
+#pragma unroll
+            for (int k = 0; k < kTail; ++k, row += 32) *row = make_double2(1.0, 0.0);   // K_B reads whole groups of planes
+            it += nrows + kTail;
             if (!done) {
                 if (broke) small = t.scan_small();         // rare path: rebuild the flags from scratch
                 else {
@@ -296,11 +301,12 @@ struct BLayout {
     static constexpr int PPW = 32 / G;                 // points per warp
     static constexpr int NPL = D - 1;                  // planes
     static constexpr int ROWS_PER_COPY = 32 / PPW;     // stream rows moved by one warp-wide cp.async
-    static constexpr int NCOPY = (NPL + ROWS_PER_COPY - 1) / ROWS_PER_COPY;
+    static constexpr int NCOPY = (NPL + kTail + ROWS_PER_COPY - 1) / ROWS_PER_COPY;
+    static constexpr int SLOT_ROWS = 2 * NPL + kTail;  // [NPL identity guard rows][NPL + kTail data rows]
     static constexpr int DH = (D + 1) / 2;             // half of the eigen-indices (a-reduction in two halves)
     static constexpr int NP = D * (D - 1) / 2;         // index pairs i < j
     // shared memory per warp, in doubles
-    static constexpr int RING = kRing * NPL * PPW * 2;                 // double2 [kRing][NPL][PPW]
+    static constexpr int RING = kRing * SLOT_ROWS * PPW * 2;           // double2 [kRing][SLOT_ROWS][PPW]
     static constexpr int HDR = kMaxRounds * PPW / 2;                   // unsigned [kMaxRounds][PPW]
     static constexpr int ZB = 2 * PPW * D * 2;                         // double2 [2][PPW][D]
     static constexpr int LV = 8 * PPW * D;                             // double [8][PPW][D]
@@ -326,7 +332,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) apply_kernel(SplitArgs a) {
     const int g = lane / G, q = lane % G;                       // point slot in the warp, lane within the point
     double* base = sm + (size_t)warp * L::PER_WARP;
     // rotation phase
-    double2* ring = reinterpret_cast<double2*>(base);                        // [kRing][NPL][PPW]
+    double2* ring = reinterpret_cast<double2*>(base);                        // [kRing][SLOT_ROWS][PPW]
     unsigned* hb = reinterpret_cast<unsigned*>(base + L::RING);              // [kMaxRounds][PPW]
     // gradient phase (aliases the rotation phase)
     double* lv = base;                                                       // [8][PPW][D]
@@ -368,8 +374,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) apply_kernel(SplitArgs a) {
 #pragma unroll
             for (int i = 0; i < D; ++i) v[k][i] = (i == q * R + k) ? 1.0 : 0.0;
 
-        // ---- stage the round headers of my PPW points: hb[r][pt]
+        // ---- identity guard rows of every ring slot (planes above a round's top), round headers of my points
         __syncwarp();
+#pragma unroll
+        for (int sl = 0; sl < kRing; ++sl)
+            for (int idx = lane; idx < NPL * PPW; idx += 32) ring[sl * L::SLOT_ROWS * PPW + idx] = make_double2(1.0, 0.0);
         for (int idx = lane; idx < nr * PPW; idx += 32) hb[idx] = hdr[(idx / PPW) * 32 + (idx % PPW)];
         __syncwarp();
 
@@ -380,8 +389,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) apply_kernel(SplitArgs a) {
             if (r < nr) {
                 const unsigned hh = hb[r * PPW];                       // uniform fields of the round
                 const int mtop_i = (hh >> 6) & 63, lbot_i = (hh >> 12) & 63, it0 = hh >> 18;
-                const int nrows = mtop_i - lbot_i;
-                double2* slot = ring + (r % kRing) * NPL * PPW;
+                const int nrows = mtop_i - lbot_i + kTail;
+                double2* slot = ring + ((r % kRing) * L::SLOT_ROWS + NPL) * PPW;
 #pragma unroll
                 for (int t = 0; t < L::NCOPY; ++t) {
                     const int j = cj0 + t * L::ROWS_PER_COPY;
@@ -394,16 +403,24 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) apply_kernel(SplitArgs a) {
         for (int r = 0; r < kRing - 1; ++r) issue(r);
         for (int r = 0; r < nr; ++r) {
             __syncwarp();                                   // everyone is done with the slot about to be refilled
+#ifndef QTET_EXP_NOISSUE
             issue(r + kRing - 1);
+#endif
             const unsigned h = hb[r * PPW + g];
             const int mtop = (h >> 6) & 63;
             const int lcur = __reduce_min_sync(0xffffffffu, (int)(h & 63));   // idle points carry l = 63
+#ifndef QTET_EXP_NOISSUE
             cp_async_wait<kRing - 1>();                     // this lane's copies of round r have landed
+#endif
             __syncwarp();
+#ifdef QTET_EXP_NOROT
+            continue;
+#endif
             if (lcur >= mtop) continue;                     // none of my points sweeps in this round
-            // plane i sits in row mtop-1-i of the slot
-            const double2* rb = ring + (r % kRing) * NPL * PPW + (mtop - 1) * PPW + g;
-            // Planes mtop-1 .. lcur, top-down, in groups of four with ONE warp-uniform exit test per group.
+            // plane i sits in data row mtop-1-i of the slot; rows above hold the identity (guard), and so do the
+            // kTail rows below the round's lowest plane and every cell a point does not touch
+            const double2* rb = ring + ((r % kRing) * L::SLOT_ROWS + NPL + mtop - 1) * PPW + g;
+            // Planes D-2 .. lcur, top-down, in groups of four with ONE warp-uniform exit test per group.
             // Inside a group the code is branch-free: (c, s) of four planes are fetched ahead of the R
             // independent dependency chains, and only one fma per row and plane sits on a chain:
             //   v[i] <- c x - s y  with  c x  computed off-chain.
@@ -413,10 +430,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) apply_kernel(SplitArgs a) {
                 if (i0 - 3 >= mtop) continue;               // whole group above the swept range (padding / split)
                 double2 cs[4];
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                    const int i = i0 - k4;
-                    cs[k4] = (i >= 0 && i < mtop && i >= lcur) ? rb[-i * PPW] : make_double2(1.0, 0.0);
-                }
+                for (int k4 = 0; k4 < 4; ++k4) cs[k4] = rb[-(((i0 - k4) >= 0) ? (i0 - k4) : 0) * PPW];
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {
                     const int i = i0 - k4;
@@ -760,6 +774,10 @@ int launch_split(const ProblemView& pv, SplitWorkspace** wsp, const double* chis
         QTET_CUDA(cudaDeviceGetAttribute(&ws->sms, cudaDevAttrMultiProcessorCount, ws->device));
         ws->D = padded_dim(d);
         ws->capit = 2 * d * d + 64;                       // stream rows per batch (warp iterations)
+        if (const char* env = std::getenv("QTET_SPLIT_CAPIT")) {   // test hook: force the overflow -> generic fallback
+            const int v = std::atoi(env);
+            if (v > 0 && v < ws->capit) ws->capit = v;
+        }
         std::vector<unsigned short> tab;
         for (int i = 0; i < ws->D; ++i)
             for (int j = i + 1; j < ws->D; ++j) tab.push_back((unsigned short)(i | (j << 8)));

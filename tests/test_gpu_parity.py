@@ -9,6 +9,8 @@ only good to ~1e-5, see tests/test_oracle.py):
     grad   : |dg|  <= GRAD_RTOL * max(1, max|g|) per point
     t_star : identical, except where the two best samples are closer than the loss tolerance
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -183,3 +185,28 @@ def test_split_and_generic_paths_agree(native):
     assert same.mean() > 0.999
     assert (np.abs(a[1] - b[1]) / np.maximum(1, np.abs(b[1]).max(axis=1, keepdims=True)))[same].max() < 1e-7
     p.close()
+
+
+def test_stream_overflow_falls_back_to_generic_kernel(tmp_path):
+    """Batches whose rotation stream does not fit its slot are recomputed by the fused generic kernel without a
+    host round trip.  QTET_SPLIT_CAPIT (test hook) shrinks the slot so that EVERY batch overflows."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = f"""
+import sys, numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'quantum-targeted-energy-transfer_b200')!r})
+from tet import _native
+from oracle import qtet_oracle as O
+c = {{"max_N": 20, "sites": 2, "max_t": 25, "omegas": [-3, 3], "chis": [0, 0], "coupling": 1, "timesteps": 30}}
+X = np.random.default_rng(9).uniform(-10, 10, (333, 2))
+p = _native.Problem.from_const(c)
+assert p.get_path() == _native.QTET_PATH_SPLIT
+L, g, k = p.loss_grad_host(X, 1)
+Lr, gr, kr = O.loss_grad_batch(c, X, 1)
+assert np.abs(L - Lr).max() < 2e-9 and (k == kr).all() and np.abs(g - gr).max() < 1e-7 * max(1, np.abs(gr).max())
+print('ok')
+"""
+    out = subprocess.run([sys.executable, "-c", code], env={**os.environ, "QTET_SPLIT_CAPIT": "7"},
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
