@@ -40,7 +40,8 @@ typedef struct qtet_problem qtet_problem;
 /* Kernel family selection for qtet_set_path (diagnostics / parity tests). */
 #define QTET_PATH_AUTO    0    /* fast split path when eligible, fused generic otherwise */
 #define QTET_PATH_GENERIC 1    /* fused CTA-per-point kernel, any system */
-#define QTET_PATH_SPLIT   2    /* thread-per-point QL + warp-per-point apply (tridiagonal, d<=32) */
+#define QTET_PATH_SPLIT   2    /* thread-per-point scalar QL + rotation replay (register path for tridiagonal d<=32,
+                                  shared-memory replay for d<=128 incl. dense H after Householder) */
 
 /*
  * Build the chi-independent part of the problem once: Fock basis in the reference's order

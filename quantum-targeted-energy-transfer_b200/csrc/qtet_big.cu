@@ -1,0 +1,371 @@
+// Split path for LARGE Fock dimensions (32 < d <= 128: dimers up to N = 127, trimer N = 10 with d = 66, ...).
+//
+//   [dense H only]  generic_kernel mode 1   CTA per point: H build + Householder -> tridiagonal + Q
+//   ql_scalar_big_kernel                    THREAD per point: two-pass QL with perfect shifts on the tridiagonal,
+//                                           rounds recorded as coalesced rows (same scheme as qtet_split.cu, with
+//                                           128-bit convergence masks and the tridiagonal in shared memory)
+//   generic_kernel mode 2                   CTA per point, thread = row of V in shared memory: replays the rounds
+//                                           on V = I (or Q), then evolution + gradient
+//
+// The fused generic kernel (mode 0) spends >90 % of its time in the serial QL recurrence, recomputed by every
+// warp of every CTA; here that recurrence runs once per point in one thread, 32 points per warp.
+#include <cstdlib>
+
+#include "qtet_big.cuh"
+
+namespace qtet {
+
+namespace {
+
+constexpr double kEps = 1.1102230246251565e-16;
+constexpr int kWarpsBig = 2;
+
+struct Mask128 {
+    unsigned long long lo = 0ull, hi = 0ull;
+    __device__ __forceinline__ void set(int k) { if (k < 64) lo |= 1ull << k; else hi |= 1ull << (k - 64); }
+    __device__ __forceinline__ void clr(int k) { if (k < 64) lo &= ~(1ull << k); else hi &= ~(1ull << (k - 64)); }
+    __device__ __forceinline__ void put(int k, bool v) { if (v) set(k); else clr(k); }
+    // first set bit at index >= l, or -1
+    __device__ __forceinline__ int first_set_ge(int l) const {
+        if (l < 64) {
+            const unsigned long long x = lo >> l;
+            if (x) return l + __ffsll((long long)x) - 1;
+            if (hi) return 64 + __ffsll((long long)hi) - 1;
+            return -1;
+        }
+        if (l >= 128) return -1;
+        const unsigned long long x = hi >> (l - 64);
+        return x ? (l + __ffsll((long long)x) - 1) : -1;
+    }
+    // first CLEAR bit at index in [l, limit), or -1
+    __device__ __forceinline__ int first_clear_ge(int l, int limit) const {
+        Mask128 inv;
+        inv.lo = ~lo; inv.hi = ~hi;
+        const int k = inv.first_set_ge(l);
+        return (k >= 0 && k < limit) ? k : -1;
+    }
+};
+
+struct BigQlArgs {
+    ProblemView pv;
+    const double* chis;       // [n, f]
+    long long n;
+    BigStream bs;
+    int use_tri;              // 1: tridiagonal comes from bs.tri_d / bs.tri_e (dense H), 0: built from chis
+    int* overflow_list;
+    int* overflow_count;
+};
+
+struct QlLaneBig {
+    double* arr;       // diag k at arr[64 k], off k at arr[64 k + 32]
+    int d;
+    __device__ __forceinline__ double& dg(int k) const { return arr[64 * k]; }
+    __device__ __forceinline__ double& of(int k) const { return arr[64 * k + 32]; }
+    __device__ __forceinline__ Mask128 scan_small() const {
+        Mask128 m;
+        m.set(d - 1);
+        for (int k = 0; k < d - 1; ++k) {
+            const double dd = fabs(dg(k)) + fabs(dg(k + 1));
+            if (fabs(of(k)) <= kEps * dd) m.set(k);
+        }
+        return m;
+    }
+    __device__ __forceinline__ double wilkinson_g(int l, int m) const {
+        const double dl = dg(l), el = of(l);
+        const double gg = (dg(l + 1) - dl) / (2.0 * el);
+        const double rr = sqrt(fma(gg, gg, 1.0));
+        return dg(m) - dl + el / (gg + copysign(rr, gg));
+    }
+};
+
+__global__ void __launch_bounds__(kWarpsBig * 32) ql_scalar_big_kernel(BigQlArgs a) {
+    extern __shared__ double sm[];
+    const ProblemView& pv = a.pv;
+    const int d = pv.d, f = pv.f;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    QlLaneBig t;
+    t.arr = sm + (size_t)warp * 2 * d * 32 + lane;
+    t.d = d;
+    const long long nbatch = (a.n + 31) / 32;
+    for (long long batch = (long long)blockIdx.x * kWarpsBig + warp; batch < nbatch; batch += (long long)gridDim.x * kWarpsBig) {
+        const long long p = batch * 32 + lane;
+        const bool valid = p < a.n;
+        const long long pc = valid ? p : a.n - 1;
+        double hchi[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hchi[k] = (k < f && !a.use_tri) ? 0.5 * a.chis[pc * f + k] : 0.0;
+        double lam[128];                                   // eigenvalue pass 1 left at each index (local memory)
+        double mean = 0.0;
+        for (int pass = 0; pass < 2; ++pass) {
+            double sum = 0.0;
+            for (int m = 0; m < d; ++m) {
+                double acc, off;
+                if (a.use_tri) {
+                    acc = a.bs.tri_d[pc * d + m];
+                    off = (m < d - 1) ? a.bs.tri_e[pc * d + m] : 0.0;
+                } else {
+                    acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if (k < f) {
+                            const double n = pv.occ[m * f + k];
+                            acc = acc + (pv.omegas[k] * n + hchi[k] * (n * n));
+                        }
+                    }
+                    off = (m < d - 1) ? pv.offd[m] : 0.0;
+                }
+                t.dg(m) = acc;
+                t.of(m) = off;
+                sum += acc;
+            }
+            if (pass == 0) mean = sum / (double)d;
+            for (int m = 0; m < d; ++m) t.dg(m) -= mean;
+            if (pass == 1) break;
+            // ---- pass 1: eigenvalues only (plain implicit QL, Wilkinson shifts)
+            Mask128 small = t.scan_small();
+            int l = 0, iter = 0;
+            while (true) {
+                const int lnew = small.first_clear_ge(l, d - 1);
+                if (lnew < 0) break;
+                if (lnew != l) iter = 0;
+                l = lnew;
+                const int m = small.first_set_ge(l);
+                if (++iter > 60) break;                    // give up quietly: pass 2 does not rely on pass 1
+                double g = t.wilkinson_g(l, m);
+                double s = 1.0, c = 1.0, pp = 0.0, dnext = 0.0;
+                bool broke = false;
+                for (int i = m - 1; i >= l; --i) {
+                    const double ei = t.of(i);
+                    const double fo = s * ei, bo = c * ei;
+                    const double r2 = fma(fo, fo, g * g);
+                    if (r2 == 0.0) { t.of(i + 1) = 0.0; t.dg(i + 1) -= pp; t.of(m) = 0.0; broke = true; break; }
+                    const double rinv = rsqrt(r2);
+                    const double r = r2 * rinv;
+                    s = fo * rinv; c = g * rinv;
+                    g = t.dg(i + 1) - pp;
+                    const double rr = fma(t.dg(i) - g, s, 2.0 * c * bo);
+                    pp = s * rr;
+                    const double dnew = g + pp;
+                    t.dg(i + 1) = dnew;
+                    g = fma(c, rr, -bo);
+                    if (i + 1 < m) {
+                        t.of(i + 1) = r;
+                        small.put(i + 1, r <= kEps * (fabs(dnew) + fabs(dnext)));
+                    }
+                    dnext = dnew;
+                }
+                if (broke) { small = t.scan_small(); continue; }
+                const double dlnew = t.dg(l) - pp;
+                t.dg(l) = dlnew; t.of(l) = g; t.of(m) = 0.0;
+                small.set(m);
+                small.put(l, fabs(g) <= kEps * (fabs(dlnew) + fabs(dnext)));
+            }
+            for (int m = 0; m < d; ++m) lam[m] = t.dg(m);
+        }
+
+        // ---- pass 2: recorded rounds, perfect shift on the first sweep at every index
+        double2* rec = a.bs.stream + (size_t)batch * a.bs.capit * 32 + lane;
+        unsigned* hdr = a.bs.hdr + (size_t)batch * a.bs.maxr * 32 + lane;
+        int* it0s = a.bs.it0 + (size_t)batch * a.bs.maxr;
+        Mask128 small = t.scan_small();
+        int it = 0, round = 0, l = 0, iter = 0, tried = -1;
+        bool overflow = false;
+        while (true) {
+            const int lnew0 = small.first_clear_ge(l, d - 1);
+            const bool done = (lnew0 < 0);
+            const int lnew = done ? d : lnew0;
+            if (lnew != l) iter = 0;
+            l = lnew;
+            if (__all_sync(0xffffffffu, done)) break;
+            const int m = done ? 0 : small.first_set_ge(l);
+            ++iter;
+            const int mtop = __reduce_max_sync(0xffffffffu, m);
+            const int lbot = __reduce_min_sync(0xffffffffu, done ? 255 : l);
+            const int nrows = mtop - lbot;
+            if (__any_sync(0xffffffffu, !done && iter > 60) || round >= a.bs.maxr - 1 || it + nrows > a.bs.capit) {
+                overflow = true;
+                break;
+            }
+            hdr[(size_t)round * 32] = (unsigned)(done ? 0xff : l) | ((unsigned)mtop << 8) | ((unsigned)lbot << 16);
+            if (lane == 0) it0s[round] = it;
+            double g = 0.0, s = 1.0, c = 1.0, pp = 0.0, dnext = 0.0;
+            if (!done) {
+                if (tried != l) { tried = l; g = t.dg(m) - lam[l]; }
+                else g = t.wilkinson_g(l, m);
+            }
+            bool broke = false;
+            // stream row it + (mtop-1-i) holds, for every lane, the rotation of plane i (identity if untouched)
+            double2* row = rec + (size_t)it * 32;
+            for (int i = mtop - 1; i >= lbot; --i, row += 32) {
+                double2 out = make_double2(1.0, 0.0);
+                if (!done && !broke && i < m && i >= l) {
+                    const double ei = t.of(i);
+                    const double fo = s * ei, bo = c * ei;
+                    const double r2 = fma(fo, fo, g * g);
+                    if (r2 == 0.0) {
+                        t.of(i + 1) = 0.0; t.dg(i + 1) -= pp; t.of(m) = 0.0;
+                        broke = true;
+                    } else {
+                        const double rinv = rsqrt(r2);
+                        const double r = r2 * rinv;
+                        s = fo * rinv; c = g * rinv;
+                        g = t.dg(i + 1) - pp;
+                        const double rr = fma(t.dg(i) - g, s, 2.0 * c * bo);
+                        pp = s * rr;
+                        const double dnew = g + pp;
+                        t.dg(i + 1) = dnew;
+                        g = fma(c, rr, -bo);
+                        if (i + 1 < m) {
+                            t.of(i + 1) = r;
+                            small.put(i + 1, r <= kEps * (fabs(dnew) + fabs(dnext)));
+                        }
+                        dnext = dnew;
+                        out = make_double2(c, s);
+                    }
+                }
+                *row = out;                                // all 32 lanes: one coalesced 512 B row
+            }
+            it += nrows;
+            if (!done) {
+                if (broke) small = t.scan_small();
+                else {
+                    const double dlnew = t.dg(l) - pp;
+                    t.dg(l) = dlnew; t.of(l) = g; t.of(m) = 0.0;
+                    small.set(m);
+                    small.put(l, fabs(g) <= kEps * (fabs(dlnew) + fabs(dnext)));
+                }
+            }
+            ++round;
+        }
+        if (lane == 0) a.bs.nrounds[batch] = overflow ? 0 : round;
+        if (valid) {
+            if (overflow) {
+                const int slot = atomicAdd(a.overflow_count, 1);
+                a.overflow_list[slot] = (int)p;
+            }
+            for (int m = 0; m < d; ++m) a.bs.ev[p * d + m] = t.dg(m);
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+struct BigWorkspace {
+    int device = 0, sms = 0, capit = 0, maxr = 0;
+    char* blob = nullptr;
+    size_t blob_bytes = 0;
+    int* overflow_count = nullptr;
+};
+
+bool big_eligible(const ProblemView& pv) {
+    if (std::getenv("QTET_NO_BIG_SPLIT")) return false;
+    if (pv.d <= 32 && pv.tridiag) return false;          // the register-resident split path is faster there
+    return pv.d >= 4 && pv.d <= 128 && pv.f <= 8;
+}
+
+void big_workspace_free(BigWorkspace* ws) {
+    if (!ws) return;
+    if (ws->blob) cudaFree(ws->blob);
+    if (ws->overflow_count) cudaFree(ws->overflow_count);
+    delete ws;
+}
+
+int launch_generic_list(const ProblemView& pv, const double* chis, const int* list, const int* count, long long max_count,
+                        int site, double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st);
+
+int launch_big(const ProblemView& pv, BigWorkspace** wsp, const double* chis, int64_t B, int site, double* loss,
+               double* grad, int32_t* tstar, double* trace, cudaStream_t st, Profiler* prof) {
+    if (B <= 0) return QTET_OK;
+    if (!big_eligible(pv)) { set_error("large-d split path not eligible for this problem"); return QTET_EUNSUPPORTED; }
+    BigWorkspace* ws = *wsp;
+    const int d = pv.d;
+    if (!ws) {
+        ws = new BigWorkspace();
+        *wsp = ws;
+        QTET_CUDA(cudaGetDevice(&ws->device));
+        QTET_CUDA(cudaDeviceGetAttribute(&ws->sms, cudaDevAttrMultiProcessorCount, ws->device));
+        ws->capit = d * d + 8 * d;                        // stream rows per batch
+        ws->maxr = (3 * d > 128) ? 3 * d : 128;
+        if (const char* env = std::getenv("QTET_SPLIT_CAPIT")) {   // test hook: force the overflow -> fused fallback
+            const int v = std::atoi(env);
+            if (v > 0 && v < ws->capit) ws->capit = v;
+        }
+        QTET_CUDA(cudaMalloc(&ws->overflow_count, sizeof(int)));
+    }
+    const bool dense = !pv.tridiag;
+    const size_t per_batch = (size_t)ws->capit * 32 * sizeof(double2) + (size_t)ws->maxr * 32 * 4 + (size_t)ws->maxr * 4 + 4 +
+                             32 * ((size_t)d * 8 + 4 + (dense ? (2 * (size_t)d * 8 + (size_t)d * d * 8) : 0));
+    long long chunk_b = (long long)((size_t)4 << 30) / (long long)per_batch;      // <= 4 GiB in flight
+    if (chunk_b < 64) chunk_b = 64;
+    const long long all_b = (B + 31) / 32;
+    if (chunk_b > all_b) chunk_b = all_b;
+    const long long chunk = chunk_b * 32;
+    auto align = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t o_hdr = align((size_t)chunk_b * ws->capit * 32 * sizeof(double2));
+    const size_t o_it0 = o_hdr + align((size_t)chunk_b * ws->maxr * 32 * 4);
+    const size_t o_nr = o_it0 + align((size_t)chunk_b * ws->maxr * 4);
+    const size_t o_ev = o_nr + align((size_t)chunk_b * 4);
+    const size_t o_list = o_ev + align((size_t)chunk * d * 8);
+    const size_t o_trid = o_list + align((size_t)chunk * 4);
+    const size_t o_trie = o_trid + (dense ? align((size_t)chunk * d * 8) : 0);
+    const size_t o_q = o_trie + (dense ? align((size_t)chunk * d * 8) : 0);
+    const size_t total = o_q + (dense ? align((size_t)chunk * d * d * 8) : 0);
+    if (total > ws->blob_bytes) {
+        if (ws->blob) { cudaDeviceSynchronize(); cudaFree(ws->blob); }
+        ws->blob = nullptr; ws->blob_bytes = 0;
+        cudaError_t e = cudaMalloc(&ws->blob, total);
+        if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(large-d workspace) failed"); return QTET_ENOMEM; }
+        ws->blob_bytes = total;
+    }
+    BigStream bs;
+    bs.stream = (double2*)ws->blob; bs.hdr = (unsigned*)(ws->blob + o_hdr); bs.it0 = (int*)(ws->blob + o_it0);
+    bs.nrounds = (int*)(ws->blob + o_nr); bs.ev = (double*)(ws->blob + o_ev);
+    bs.capit = ws->capit; bs.maxr = ws->maxr;
+    if (dense) { bs.tri_d = (double*)(ws->blob + o_trid); bs.tri_e = (double*)(ws->blob + o_trie); bs.qmat = (double*)(ws->blob + o_q); }
+    int* overflow_list = (int*)(ws->blob + o_list);
+
+    const size_t smemA = (size_t)kWarpsBig * 2 * d * 32 * sizeof(double);
+    QTET_CUDA(cudaFuncSetAttribute(ql_scalar_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+    QTET_CUDA(cudaFuncSetAttribute(ql_scalar_big_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    int per_sm_a = 0;
+    QTET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, ql_scalar_big_kernel, kWarpsBig * 32, smemA));
+    if (per_sm_a < 1) per_sm_a = 1;
+
+    for (long long lo = 0; lo < B; lo += chunk) {
+        const long long n = (B - lo < chunk) ? (B - lo) : chunk;
+        const double* cchis = chis + lo * pv.f;
+        double* closs = loss ? loss + lo : nullptr;
+        double* cgrad = grad ? grad + lo * pv.f : nullptr;
+        int32_t* cts = tstar ? tstar + lo : nullptr;
+        double* ctrace = trace ? trace + lo * pv.T : nullptr;
+        int rc;
+        if (dense) {
+            if (prof) prof->begin(2, n, st);
+            rc = launch_generic_mode(pv, cchis, n, site, nullptr, nullptr, nullptr, nullptr, st, 1, bs);
+            if (prof) prof->finish(2, st);
+            if (rc) return rc;
+        }
+        QTET_CUDA(cudaMemsetAsync(ws->overflow_count, 0, sizeof(int), st));
+        BigQlArgs qa;
+        qa.pv = pv; qa.chis = cchis; qa.n = n; qa.bs = bs; qa.use_tri = dense ? 1 : 0;
+        qa.overflow_list = overflow_list; qa.overflow_count = ws->overflow_count;
+        long long gridA = (long long)ws->sms * per_sm_a;
+        const long long needA = ((n + 31) / 32 + kWarpsBig - 1) / kWarpsBig;
+        if (gridA > needA) gridA = needA;
+        if (prof) prof->begin(0, n, st);
+        ql_scalar_big_kernel<<<(unsigned)gridA, kWarpsBig * 32, smemA, st>>>(qa);
+        count_launch();
+        if (prof) prof->finish(0, st);
+        QTET_CUDA(cudaGetLastError());
+        if (prof) prof->begin(1, n, st);
+        rc = launch_generic_mode(pv, cchis, n, site, closs, cgrad, cts, ctrace, st, 2, bs);
+        if (prof) prof->finish(1, st);
+        if (rc) return rc;
+        rc = launch_generic_list(pv, cchis, overflow_list, ws->overflow_count, n, site, closs, cgrad, cts, ctrace, st);
+        if (rc) return rc;
+    }
+    return QTET_OK;
+}
+
+}  // namespace qtet

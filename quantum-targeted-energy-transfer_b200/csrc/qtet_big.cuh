@@ -1,0 +1,25 @@
+// Hand-off between the scalar QL kernel for large Fock dimensions (qtet_big.cu) and the replay mode of the
+// generic kernel (qtet_generic.cu).
+#pragma once
+#include "qtet_common.cuh"
+
+namespace qtet {
+
+struct BigStream {
+    // written by the scalar QL kernel, read by the replay
+    double2* stream = nullptr;     // [nb][capit][32]  one 512 B row per plane of a round: (c, s) per lane
+    unsigned* hdr = nullptr;       // [nb][maxr][32]   l (0xff = idle) | mtop << 8 | lbot << 16
+    int* it0 = nullptr;            // [nb][maxr]       first stream row of the round
+    int* nrounds = nullptr;        // [nb]
+    double* ev = nullptr;          // [n][d]           eigenvalues (shifted by the mean of the diagonal)
+    int capit = 0, maxr = 0;
+    // dense H only: Householder tridiagonalisation (generic kernel, mode 1)
+    double* tri_d = nullptr;       // [n][d]
+    double* tri_e = nullptr;       // [n][d]
+    double* qmat = nullptr;        // [n][d][d]
+};
+
+int launch_generic_mode(const ProblemView& pv, const double* chis, int64_t B, int site, double* loss, double* grad,
+                        int32_t* tstar, double* trace, cudaStream_t st, int mode, const BigStream& bs);
+
+}  // namespace qtet

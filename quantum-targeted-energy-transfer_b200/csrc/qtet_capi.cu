@@ -47,6 +47,8 @@ int ensure_scratch(qtet_problem* p, size_t bytes) {
 
 int loss_grad_dispatch(qtet_problem* p, const double* chis, int64_t B, int site, double* loss,
                        double* grad, int32_t* tstar, double* trace, cudaStream_t st) {
+    if (p->path == QTET_PATH_SPLIT && !split_eligible(p->view))
+        return launch_big(p->view, &p->big_ws, chis, B, site, loss, grad, tstar, trace, st, p->prof.on ? &p->prof : nullptr);
     if (p->path == QTET_PATH_SPLIT)
         return launch_split(p->view, &p->split_ws, chis, B, site, loss, grad, tstar, trace, st, p->prof.on ? &p->prof : nullptr);
     return launch_generic(p->view, chis, B, site, loss, grad, tstar, trace, st, p->prof.on ? &p->prof : nullptr);
@@ -150,7 +152,7 @@ int qtet_problem_create(int max_N, int sites, const double* omegas, double coupl
     v.N = max_N; v.f = sites; v.d = d; v.T = timesteps; v.tridiag = p->tridiag ? 1 : 0; v.max_t = max_t;
     v.lin = p->dev_blob + o_lin; v.quad = p->dev_blob + o_quad; v.occ = p->dev_blob + o_occ;
     v.offd = p->dev_blob + o_off; v.tgrid = p->dev_blob + o_t; v.omegas = p->dev_blob + o_om;
-    p->path = split_eligible(v) ? QTET_PATH_SPLIT : QTET_PATH_GENERIC;
+    p->path = (split_eligible(v) || big_eligible(v)) ? QTET_PATH_SPLIT : QTET_PATH_GENERIC;
     *out = p;
     return QTET_OK;
 }
@@ -161,6 +163,7 @@ void qtet_problem_destroy(qtet_problem* p) {
     if (p->dev_blob) cudaFree(p->dev_blob);
     if (p->scratch) cudaFree(p->scratch);
     split_workspace_free(p->split_ws);
+    big_workspace_free(p->big_ws);
     p->prof.clear();
     delete p;
 }
@@ -181,10 +184,10 @@ int qtet_problem_time_grid(const qtet_problem* p, double* t_host) {
 
 int qtet_set_path(qtet_problem* p, int path) {
     if (!p) { set_error("null handle"); return QTET_EINVAL; }
-    if (path == QTET_PATH_AUTO) { p->path = split_eligible(p->view) ? QTET_PATH_SPLIT : QTET_PATH_GENERIC; return QTET_OK; }
+    if (path == QTET_PATH_AUTO) { p->path = (split_eligible(p->view) || big_eligible(p->view)) ? QTET_PATH_SPLIT : QTET_PATH_GENERIC; return QTET_OK; }
     if (path == QTET_PATH_GENERIC) { p->path = path; return QTET_OK; }
     if (path == QTET_PATH_SPLIT) {
-        if (!split_eligible(p->view)) { set_error("split path needs a tridiagonal H with dim <= 32"); return QTET_EUNSUPPORTED; }
+        if (!split_eligible(p->view) && !big_eligible(p->view)) { set_error("split path needs dim <= 128"); return QTET_EUNSUPPORTED; }
         p->path = path;
         return QTET_OK;
     }

@@ -74,6 +74,12 @@ int launch_split(const ProblemView& pv, SplitWorkspace** ws, const double* chis,
                  double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st, Profiler* prof = nullptr);
 void split_workspace_free(SplitWorkspace* ws);
 
+struct BigWorkspace;     // large-d split path (qtet_big.cu)
+bool big_eligible(const ProblemView& pv);
+int launch_big(const ProblemView& pv, BigWorkspace** ws, const double* chis, int64_t B, int site, double* loss,
+               double* grad, int32_t* tstar, double* trace, cudaStream_t st, Profiler* prof = nullptr);
+void big_workspace_free(BigWorkspace* ws);
+
 int launch_argmin(const double* v, int64_t B, double* min_out, int64_t* idx_out, cudaStream_t st);
 
 struct AdamState;        // per-guess optimiser state on the device (qtet_adam.cu)
@@ -89,6 +95,7 @@ struct qtet_problem {
     double* dev_blob = nullptr;             // one allocation holding every constant array
     qtet::ProblemView view{};
     qtet::SplitWorkspace* split_ws = nullptr;
+    qtet::BigWorkspace* big_ws = nullptr;
     qtet::Profiler prof;
     // scratch for *_host convenience calls and the optimiser
     void* scratch = nullptr;

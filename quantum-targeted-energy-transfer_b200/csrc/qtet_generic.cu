@@ -13,6 +13,7 @@
 // This kernel is the general/robust path (trimer, large dimers) and the on-GPU cross-check of the
 // fast split path in qtet_split.cu.
 #include "qtet_common.cuh"
+#include "qtet_big.cuh"
 
 namespace qtet {
 
@@ -34,6 +35,12 @@ struct GenericArgs {
     double* trace;
     const int* list;      // optional: evaluate only points list[0 .. *count)
     const int* count;
+    // mode 0: fused (H build, [Householder], QL, evolution, gradient)
+    // mode 1: H build + Householder only -> tri_d / tri_e / qmat           (dense H, feeds the scalar QL kernel)
+    // mode 2: eigenvectors by REPLAYING the rotation stream of the scalar QL kernel on V = I (or Q), then
+    //         evolution + gradient as in mode 0
+    int mode;
+    BigStream bs;
 };
 
 __device__ __forceinline__ double block_sum(double v, double* red, int tid, int nwarps) {
@@ -78,12 +85,73 @@ __global__ void generic_kernel(GenericArgs a) {
         const double* chi = a.chis + b * f;
         __syncthreads();
         // ---------------------------------------------------------------- H build
-        // V <- identity
-        for (int idx = tid; idx < d * d; idx += nth) {
-            const int r = idx / d, c = idx - r * d;
-            V[r * ld + c] = (r == c) ? 1.0 : 0.0;
+        // V <- identity   (mode 2, dense H: V <- Q of the Householder reduction done by the mode-1 launch)
+        if (a.mode == 2 && !pv.tridiag) {
+            const double* q = a.bs.qmat + (size_t)b * d * d;
+            for (int idx = tid; idx < d * d; idx += nth) {
+                const int r = idx / d, c = idx - r * d;
+                V[r * ld + c] = q[idx];
+            }
+        } else {
+            for (int idx = tid; idx < d * d; idx += nth) {
+                const int r = idx / d, c = idx - r * d;
+                V[r * ld + c] = (r == c) ? 1.0 : 0.0;
+            }
         }
-        if (pv.tridiag) {
+        if (a.mode == 2) {
+            // ------------------------------------------------------------ replay of the recorded rounds
+            // thread = row of V.  A round's (c, s) of my point are staged in shared memory (double-buffered,
+            // next round prefetched into a register); every row then walks the planes top-down keeping the
+            // chain element in a register: one LDS + one STS + four FP64 per plane.
+            __syncthreads();
+            const long long batch = b >> 5;
+            const int blane = (int)(b & 31);
+            const int nr = a.bs.nrounds[batch];
+            const double2* rec = a.bs.stream + (size_t)batch * a.bs.capit * 32 + blane;
+            const unsigned* hdr = a.bs.hdr + (size_t)batch * a.bs.maxr * 32 + blane;
+            const int* it0s = a.bs.it0 + (size_t)batch * a.bs.maxr;
+            double2* csb = reinterpret_cast<double2*>(M + (((size_t)d * ld) & 1));   // [2][d], 16 B aligned (M is free until the gradient)
+            unsigned h = (nr > 0) ? hdr[0] : 0u;
+            int it0 = (nr > 0) ? it0s[0] : 0;
+            double2 pre = make_double2(1.0, 0.0);
+            {
+                const int l0 = h & 0xff, mt0 = (h >> 8) & 0xff;
+                if (nr > 0 && l0 != 0xff && tid < mt0 - l0) pre = rec[(size_t)(it0 + tid) * 32];
+            }
+            for (int r = 0; r < nr; ++r) {
+                const int lp = h & 0xff, mtop = (h >> 8) & 0xff;
+                const int cnt = (lp == 0xff) ? 0 : (mtop - lp);
+                double2* cs = csb + (r & 1) * d;
+                if (tid < cnt) cs[tid] = pre;
+                // prefetch the next round
+                unsigned hn = 0u; int it0n = 0;
+                pre = make_double2(1.0, 0.0);
+                if (r + 1 < nr) {
+                    hn = hdr[(size_t)(r + 1) * 32];
+                    it0n = it0s[r + 1];
+                    const int ln = hn & 0xff, mtn = (hn >> 8) & 0xff;
+                    if (ln != 0xff && tid < mtn - ln) pre = rec[(size_t)(it0n + tid) * 32];
+                }
+                __syncthreads();
+                if (cnt > 0) {
+                    for (int row = tid; row < d; row += nth) {
+                        double* vr = V + (size_t)row * ld;
+                        double w = vr[mtop];
+                        for (int j = 0; j < cnt; ++j) {
+                            const int i = mtop - 1 - j;
+                            const double2 c_s = cs[j];
+                            const double x = vr[i];
+                            vr[i + 1] = fma(c_s.x, w, c_s.y * x);
+                            w = fma(-c_s.y, w, c_s.x * x);
+                        }
+                        vr[lp] = w;
+                    }
+                }
+                h = hn; it0 = it0n;
+            }
+            __syncthreads();
+            for (int i = tid; i < d; i += nth) wdiag[i] = a.bs.ev[(size_t)b * d + i];
+        } else if (pv.tridiag) {
             for (int m = lane; m < d; m += 32) {
                 double acc = 0.0;
                 for (int k = 0; k < f; ++k)
@@ -163,12 +231,21 @@ __global__ void generic_kernel(GenericArgs a) {
                 woff[w * d + d - 1] = 0.0;
             }
             __syncthreads();
+            if (a.mode == 1) {
+                for (int i = tid; i < d; i += nth) { a.bs.tri_d[(size_t)b * d + i] = wdiag[i]; a.bs.tri_e[(size_t)b * d + i] = woff[i]; }
+                double* q = a.bs.qmat + (size_t)b * d * d;
+                for (int idx = tid; idx < d * d; idx += nth) {
+                    const int r = idx / d, c = idx - r * d;
+                    q[idx] = V[r * ld + c];
+                }
+                continue;
+            }
         }
 
         // ---------------------------------------------------------------- implicit QL
         // Scalar recurrences are computed redundantly by every lane on the warp-private copy;
         // each thread rotates its own rows of V.  (Algorithm: implicit-shift QL with Wilkinson shift.)
-        {
+        if (a.mode == 0) {
             double* dg = mydiag;
             double* of = myoff;
             for (int l = 0; l < d; ++l) {
@@ -359,7 +436,8 @@ size_t generic_smem_bytes(int d, int nthreads) {
 }
 
 static int launch_generic_impl(const ProblemView& pv, const double* chis, int64_t B, const int* list, const int* count,
-                               int site, double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st) {
+                               int site, double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st,
+                               int mode = 0, const BigStream* bs = nullptr) {
     if (B <= 0) return QTET_OK;
     if (pv.f > 8) { set_error("generic kernel supports at most 8 sites"); return QTET_EUNSUPPORTED; }
     const int nth = generic_threads(pv.d);
@@ -383,6 +461,8 @@ static int launch_generic_impl(const ProblemView& pv, const double* chis, int64_
     a.pv = pv; a.chis = chis; a.B = B; a.site = site; a.acceptor = (site == pv.f - 1) ? 1 : 0;
     a.ldv = generic_ld(pv.d); a.loss = loss; a.grad = grad; a.tstar = tstar; a.trace = trace;
     a.list = list; a.count = count;
+    a.mode = mode;
+    if (bs) a.bs = *bs; else a.bs = BigStream{};
     if (list) { grid = 2LL * sms; if (grid > B) grid = B; }
     generic_kernel<<<(unsigned)grid, nth, smem, st>>>(a);
     count_launch();
@@ -402,6 +482,11 @@ int launch_generic(const ProblemView& pv, const double* chis, int64_t B, int sit
 int launch_generic_list(const ProblemView& pv, const double* chis, const int* list, const int* count, long long max_count,
                         int site, double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st) {
     return launch_generic_impl(pv, chis, max_count, list, count, site, loss, grad, tstar, trace, st);
+}
+
+int launch_generic_mode(const ProblemView& pv, const double* chis, int64_t B, int site, double* loss, double* grad,
+                        int32_t* tstar, double* trace, cudaStream_t st, int mode, const BigStream& bs) {
+    return launch_generic_impl(pv, chis, B, nullptr, nullptr, site, loss, grad, tstar, trace, st, mode, &bs);
 }
 
 int launch_build_h(const ProblemView& pv, const double* chis, double* H, cudaStream_t st) {
