@@ -7,7 +7,8 @@ sys.path.insert(0, os.path.join(ROOT, "quantum-targeted-energy-transfer_b200"))
 import torch
 from tet import _native
 cases = [("dimer N=4", 4, [-3, 3], 1 << 20), ("dimer N=10", 10, [-3, 3], 1 << 20), ("dimer N=31", 31, [-3, 3], 1 << 18),
-         ("dimer N=100", 100, [-3, 3], 1 << 13), ("trimer N=4", 4, [-3, 3, 3], 1 << 16), ("trimer N=10", 10, [-3, 3, 3], 1 << 14)]
+         ("dimer N=100", 100, [-3, 3], 1 << 16), ("trimer N=4", 4, [-3, 3, 3], 1 << 18), ("trimer N=10", 10, [-3, 3, 3], 1 << 17),
+         ("4-site chain N=3", 3, [-3, 0, 1, 3], 1 << 18)]
 for name, N, om, B in cases:
     const = {"max_N": N, "sites": len(om), "max_t": 25, "omegas": om, "chis": [0] * len(om), "coupling": 1, "timesteps": 30}
     prob = _native.Problem.from_const(const)
