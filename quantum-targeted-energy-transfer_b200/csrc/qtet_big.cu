@@ -1,4 +1,4 @@
-// Split path for LARGE Fock dimensions (32 < d <= 128: dimers up to N = 127, trimer N = 10 with d = 66, ...).
+// Split path for LARGE Fock dimensions (32 < d <= 115: dimers up to N = 114, trimer N = 10 with d = 66, ...).
 //
 //   [dense H only]  generic_kernel mode 1   CTA per point: H build + Householder -> tridiagonal + Q
 //   ql_scalar_big_kernel                    THREAD per point: two-pass QL with perfect shifts on the tridiagonal,
@@ -261,7 +261,7 @@ struct BigWorkspace {
 bool big_eligible(const ProblemView& pv) {
     if (std::getenv("QTET_NO_BIG_SPLIT")) return false;
     if (pv.d <= 32 && pv.tridiag) return false;          // the register-resident split path is faster there
-    return pv.d >= 4 && pv.d <= 128 && pv.f <= 8;
+    return pv.d >= 4 && pv.d <= 115 && pv.f <= 8;         // 115: V and K must both fit 227 KB of shared memory
 }
 
 void big_workspace_free(BigWorkspace* ws) {

@@ -210,3 +210,20 @@ print('ok')
     out = subprocess.run([sys.executable, "-c", code], env={**os.environ, "QTET_SPLIT_CAPIT": "7"},
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_large_dimension_limits(native, O):
+    """d = 115 (dimer N = 114) is the largest Fock space whose V and K fit shared memory; beyond it the library
+    refuses loudly instead of silently doing something else."""
+    c = make_const(114)
+    X = np.array([[0.05, -0.05], [1.0, 2.0]])
+    p = native.Problem.from_const(c)
+    assert p.dim == 115 and p.get_path() == native.QTET_PATH_SPLIT
+    L, g, k = p.loss_grad_host(X, 1)
+    Lr, gr, kr = O.loss_grad_batch(c, X, 1)
+    assert np.abs(L - Lr).max() < 5e-9 and (k == kr).all()
+    p.close()
+    big = native.Problem.from_const(make_const(130))
+    with pytest.raises(native.QtetError, match="shared memory"):
+        big.loss_grad(np.array([[0.1, -0.1]]))
+    big.close()
