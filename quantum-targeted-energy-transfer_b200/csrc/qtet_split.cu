@@ -701,6 +701,7 @@ int launch_apply(const SplitArgs& a, int sms, cudaStream_t st) {
     int per_sm = 0;
     QTET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
     if (per_sm < 1) per_sm = 1;
+    if (const char* env = std::getenv("QTET_KB_CTAS_PER_SM")) { const int v = std::atoi(env); if (v > 0 && v < per_sm) per_sm = v; }
     long long grid = (long long)sms * per_sm;
     const long long ntask = ((a.n + 31) / 32) * G;
     const long long need = (ntask + WARPS - 1) / WARPS;
@@ -828,6 +829,7 @@ int launch_split(const ProblemView& pv, SplitWorkspace** wsp, const double* chis
     int per_sm_a = 0;
     QTET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, ql_scalar_kernel, kWarpsA * 32, smemA));
     if (per_sm_a < 1) per_sm_a = 1;
+    if (const char* env = std::getenv("QTET_KA_CTAS_PER_SM")) { const int v = std::atoi(env); if (v > 0 && v < per_sm_a) per_sm_a = v; }
 
     // fork: the auxiliary stream starts after everything already queued on the caller's stream
     QTET_CUDA(cudaEventRecord(ws->ev_fork, st));
