@@ -33,7 +33,6 @@ constexpr int kMaxRounds = 128;            // header rows per batch
 constexpr int kWarpsA = 4;                 // warps per CTA, scalar kernel
 constexpr int kRing = 4;                   // rounds of rotation records in flight per warp (K_B)
 constexpr int kTail = 3;                   // identity rows appended to every round (K_B sweeps planes in groups of 4)
-constexpr unsigned kIdle = 63u;            // l field of a lane that takes no part in the round
 
 struct SplitArgs {
     ProblemView pv;
@@ -194,7 +193,7 @@ __global__ void __launch_bounds__(kWarpsA * 32) ql_scalar_kernel(SplitArgs a) {
                 overflow = true;
                 break;
             }
-            hdr[round * 32] = (unsigned)(done ? 63 : l) | ((unsigned)mtop << 6) | ((unsigned)lbot << 12) | ((unsigned)it << 18);
+            hdr[round * 32] = (unsigned)(done ? 63 : l)   /* 63 = idle */ | ((unsigned)mtop << 6) | ((unsigned)lbot << 12) | ((unsigned)it << 18);
             double g = 0.0, s = 1.0, c = 1.0, pp = 0.0, dnext = 0.0;
             if (!done) {
                 if (tried != l) { tried = l; g = t.dg(m) - lam[l]; }    // perfect shift, first sweep at this index
@@ -403,19 +402,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) apply_kernel(SplitArgs a) {
         for (int r = 0; r < kRing - 1; ++r) issue(r);
         for (int r = 0; r < nr; ++r) {
             __syncwarp();                                   // everyone is done with the slot about to be refilled
-#ifndef QTET_EXP_NOISSUE
             issue(r + kRing - 1);
-#endif
             const unsigned h = hb[r * PPW + g];
             const int mtop = (h >> 6) & 63;
             const int lcur = __reduce_min_sync(0xffffffffu, (int)(h & 63));   // idle points carry l = 63
-#ifndef QTET_EXP_NOISSUE
             cp_async_wait<kRing - 1>();                     // this lane's copies of round r have landed
-#endif
             __syncwarp();
-#ifdef QTET_EXP_NOROT
-            continue;
-#endif
             if (lcur >= mtop) continue;                     // none of my points sweeps in this round
             // plane i sits in data row mtop-1-i of the slot; rows above hold the identity (guard), and so do the
             // kTail rows below the round's lowest plane and every cell a point does not touch
