@@ -256,6 +256,8 @@ struct BigWorkspace {
     char* blob = nullptr;
     size_t blob_bytes = 0;
     int* overflow_count = nullptr;
+    unsigned short* pair_tab = nullptr;   // register-resident replay: index pairs of the padded dimension
+    int regD = 0;                         // padded dimension of the register-resident kernels, 0 = shared-memory kernels
 };
 
 bool big_eligible(const ProblemView& pv) {
@@ -268,6 +270,7 @@ void big_workspace_free(BigWorkspace* ws) {
     if (!ws) return;
     if (ws->blob) cudaFree(ws->blob);
     if (ws->overflow_count) cudaFree(ws->overflow_count);
+    if (ws->pair_tab) cudaFree(ws->pair_tab);
     delete ws;
 }
 
@@ -292,6 +295,16 @@ int launch_big(const ProblemView& pv, BigWorkspace** wsp, const double* chis, in
             if (v > 0 && v < ws->capit) ws->capit = v;
         }
         QTET_CUDA(cudaMalloc(&ws->overflow_count, sizeof(int)));
+        // rows in registers when the dimension fits (d <= 101); QTET_BIG_SMEM=1 keeps the shared-memory kernels (cross-check)
+        ws->regD = (std::getenv("QTET_BIG_SMEM") || pv.T > bigreg_max_timesteps()) ? 0 : bigreg_padded_dim(d);
+        if (ws->regD) {
+            std::vector<unsigned short> tab;
+            for (int i = 0; i < ws->regD; ++i)
+                for (int j = i + 1; j < ws->regD; ++j) tab.push_back((unsigned short)(i | (j << 8)));
+            if (tab.empty()) tab.push_back(0);
+            QTET_CUDA(cudaMalloc(&ws->pair_tab, tab.size() * sizeof(unsigned short)));
+            QTET_CUDA(cudaMemcpy(ws->pair_tab, tab.data(), tab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+        }
     }
     const bool dense = !pv.tridiag;
     const size_t per_batch = (size_t)ws->capit * 32 * sizeof(double2) + (size_t)ws->maxr * 32 * 4 + (size_t)ws->maxr * 4 + 4 +
@@ -342,7 +355,8 @@ int launch_big(const ProblemView& pv, BigWorkspace** wsp, const double* chis, in
         int rc;
         if (dense) {
             if (prof) prof->begin(2, n, st);
-            rc = launch_generic_mode(pv, cchis, n, site, nullptr, nullptr, nullptr, nullptr, st, 1, bs);
+            rc = ws->regD ? launch_hh_reg(pv, cchis, n, bs, ws->sms, st)
+                          : launch_generic_mode(pv, cchis, n, site, nullptr, nullptr, nullptr, nullptr, st, 1, bs);
             if (prof) prof->finish(2, st);
             if (rc) return rc;
         }
@@ -359,7 +373,8 @@ int launch_big(const ProblemView& pv, BigWorkspace** wsp, const double* chis, in
         if (prof) prof->finish(0, st);
         QTET_CUDA(cudaGetLastError());
         if (prof) prof->begin(1, n, st);
-        rc = launch_generic_mode(pv, cchis, n, site, closs, cgrad, cts, ctrace, st, 2, bs);
+        rc = ws->regD ? launch_replay_reg(pv, cchis, n, site, bs, ws->pair_tab, closs, cgrad, cts, ctrace, ws->sms, st)
+                      : launch_generic_mode(pv, cchis, n, site, closs, cgrad, cts, ctrace, st, 2, bs);
         if (prof) prof->finish(1, st);
         if (rc) return rc;
         rc = launch_generic_list(pv, cchis, overflow_list, ws->overflow_count, n, site, closs, cgrad, cts, ctrace, st);

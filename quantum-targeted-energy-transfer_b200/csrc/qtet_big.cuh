@@ -19,6 +19,14 @@ struct BigStream {
     double* qmat = nullptr;        // [n][d][d]
 };
 
+// register-resident kernels (qtet_bigreg.cu); they store / expect Q column-major
+int bigreg_padded_dim(int d);
+int bigreg_max_timesteps();
+int launch_hh_reg(const ProblemView& pv, const double* chis, int64_t n, const BigStream& bs, int sms, cudaStream_t st);
+int launch_replay_reg(const ProblemView& pv, const double* chis, int64_t n, int site, const BigStream& bs,
+                      const unsigned short* pair_tab, double* loss, double* grad, int32_t* tstar, double* trace, int sms,
+                      cudaStream_t st);
+
 int launch_generic_mode(const ProblemView& pv, const double* chis, int64_t B, int site, double* loss, double* grad,
                         int32_t* tstar, double* trace, cudaStream_t st, int mode, const BigStream& bs);
 

@@ -1,0 +1,710 @@
+// Register-resident kernels of the large-d split path (qtet_big.cu): one CTA per parameter point, one THREAD per
+// row, and that row (of the dense matrix A, of the Householder factor Q, of the eigenvector matrix V) lives in
+// REGISTERS for the whole phase.  Everything a row needs from the others is a broadcast operand read from shared
+// memory with LDS.128 (two operands per load, each feeding one or two DFMAs), so the FP64 pipe rather than the
+// shared-memory crossbar is the busy unit -- the shared-memory formulation these kernels replace needed two LDS
+// per DFMA and ran at 3-15 % of the FP64 peak.
+//
+//   hh_reg_kernel<D, NW>      dense H only (trimer, chains): H build (HamiltonianLoss.py:124-176), Householder
+//                             tridiagonalisation with the row of A in registers, then the forward accumulation of
+//                             Q = H_0 H_1 ... in the same registers; writes (diag, off) and Q (column-major).
+//   replay_reg_kernel<D, NW>  V <- I (or Q); replays the plane rotations recorded by ql_scalar_big_kernel on the
+//                             register rows (statically indexed, plane groups skipped with warp-uniform branches),
+//                             then psi(t) = V (c . exp(-i e t)) (HamiltonianLoss.py:204-215), loss (:227-231) and the
+//                             analytic gradient through the symmetrised Daleckii-Krein kernel (replaces Optimizer.py:85-91).
+//
+// D is the compile-time padded dimension (register arrays must be statically indexed), NW = ceil(D / 32) warps.
+#include <cstdlib>
+#include <type_traits>
+#include <utility>
+
+#include "qtet_big.cuh"
+
+namespace qtet {
+
+namespace {
+
+constexpr int kRingR = 4;      // rounds of (c, s) in flight per CTA (cp.async ring)
+constexpr int kTC = 16;        // time samples per evolution chunk
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+
+struct RegArgs {
+    ProblemView pv;
+    const double* chis;
+    long long n;
+    int site, acceptor;
+    BigStream bs;
+    const unsigned short* pair_tab;   // [D(D-1)/2]  i | j << 8, lexicographic (i, j > i)
+    double* loss; double* grad; int* tstar; double* trace;
+};
+
+// a[k] and a[k+1] of a register array for a CTA-uniform dynamic k: a jump table, not D predicated moves.
+template <int K, int D>
+__device__ __forceinline__ double elem(const double (&a)[D]) {
+    if constexpr (K < D) return a[K];
+    else return 0.0;
+}
+#define QTET_PICK_CASE(K) case K: x = elem<K>(a); y = elem<K + 1>(a); break;
+#define QTET_PICK_8(K) QTET_PICK_CASE(K) QTET_PICK_CASE(K + 1) QTET_PICK_CASE(K + 2) QTET_PICK_CASE(K + 3) \
+                       QTET_PICK_CASE(K + 4) QTET_PICK_CASE(K + 5) QTET_PICK_CASE(K + 6) QTET_PICK_CASE(K + 7)
+template <int D>
+__device__ __forceinline__ void pick2(const double (&a)[D], int k, double& x, double& y) {
+    x = 0.0; y = 0.0;
+    switch (k) {
+        QTET_PICK_8(0) QTET_PICK_8(8) QTET_PICK_8(16) QTET_PICK_8(24) QTET_PICK_8(32) QTET_PICK_8(40) QTET_PICK_8(48) QTET_PICK_8(56)
+        QTET_PICK_8(64) QTET_PICK_8(72) QTET_PICK_8(80) QTET_PICK_8(88) QTET_PICK_8(96) QTET_PICK_8(104) QTET_PICK_8(112) QTET_PICK_8(120)
+        default: break;
+    }
+}
+
+// compile-time loop: f(integral_constant<int, 0>) ... f(integral_constant<int, N-1>) (forces full expansion where
+// `#pragma unroll` gives up on thousands of iterations)
+template <class F, int... Is>
+__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, Is...>) { (f(std::integral_constant<int, Is>{}), ...); }
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f) { static_for_impl(f, std::make_integer_sequence<int, N>{}); }
+
+template <int NW>
+__device__ __forceinline__ double cta_sum(double v, double* red, int lane, int warp) {
+    v = warp_sum(v);
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += red[w];
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Householder tridiagonalisation + Q, rows in registers
+// ------------------------------------------------------------------------------------------------
+template <int D>
+struct HhLayout {
+    static constexpr int DP = (D + 3) & ~3;
+    // doubles
+    static constexpr int XS = 0;                   // [2][DP]  raw column below the diagonal (zeros above)
+    static constexpr int VS = XS + 2 * DP;         // [2][DP]  reflector
+    static constexpr int PS = VS + 2 * DP;         // [2][DP]  p = beta A v
+    static constexpr int DIAG = PS + 2 * DP;       // [DP]
+    static constexpr int OFF = DIAG + DP;          // [DP]
+    static constexpr int BETA = OFF + DP;          // [DP]
+    static constexpr int RED = BETA + DP;          // [2][2][8] partial sums + [2] x0
+    static constexpr int REFL = RED + 40;          // [D][DP]
+    static constexpr int TOTAL = REFL + D * DP;
+};
+
+template <int D, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) hh_reg_kernel(RegArgs a_) {
+    using L = HhLayout<D>;
+    constexpr int DP = L::DP;
+    extern __shared__ __align__(16) double sm[];
+    const ProblemView& pv = a_.pv;
+    const int d = pv.d, f = pv.f;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row = tid;
+    double* xs = sm + L::XS;
+    double* vs = sm + L::VS;
+    double* ps = sm + L::PS;
+    double* s_diag = sm + L::DIAG;
+    double* s_off = sm + L::OFF;
+    double* s_beta = sm + L::BETA;
+    double* red = sm + L::RED;
+    double* refl = sm + L::REFL;
+
+    for (long long b = blockIdx.x; b < a_.n; b += gridDim.x) {
+        const double* chi = a_.chis + b * f;
+        __syncthreads();
+        // ---- my row of H: hopping part (symmetric, so column `row` read coalesced) + diagonal
+        double a[D];
+        {
+            double dg = 0.0;
+            if (row < d)
+                for (int k = 0; k < f; ++k)
+                    dg = dg + (pv.omegas[k] * pv.occ[row * f + k] + (0.5 * chi[k]) * (pv.occ[row * f + k] * pv.occ[row * f + k]));
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                double h = 0.0;
+                if (row < d && j < d) h = (j == row) ? dg : pv.offd[(size_t)j * d + row];
+                a[j] = h;
+            }
+        }
+        if (row < DP) { xs[row] = 0.0; xs[DP + row] = 0.0; vs[row] = 0.0; vs[DP + row] = 0.0; ps[row] = 0.0; ps[DP + row] = 0.0; }
+
+        // ---- reduction: two CTA barriers per column
+        for (int k = 0; k < d - 2; ++k) {
+            const int par = k & 1;
+            double* xsp = xs + par * DP;
+            double* vsp = vs + par * DP;
+            double* psp = ps + par * DP;
+            double* redp = red + par * 18;
+            double x, y;
+            pick2<D>(a, k, x, y);                        // A[row][k], A[row][k+1]
+            if (row == k) s_diag[k] = x;
+            const double xi = (row > k && row < d) ? x : 0.0;
+            if (row < DP) { xsp[row] = xi; vsp[row] = xi; }
+            {
+                double part = (row > k + 1) ? xi * xi : 0.0;
+                part = warp_sum(part);
+                if (lane == 0) redp[warp] = part;
+                if (row == k + 1) redp[16] = xi;
+            }
+            __syncthreads();                             // #1
+            double sigma = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) sigma += redp[w];
+            const double x0 = redp[16];
+            if (sigma == 0.0) {                          // nothing to annihilate in this column (CTA-uniform)
+                if (tid == 0) { s_off[k] = x0; s_beta[k] = 0.0; }
+                continue;
+            }
+            const double mu = sqrt(fma(x0, x0, sigma));
+            const double alpha = (x0 >= 0.0) ? -mu : mu;
+            const double v0 = x0 - alpha;
+            const double beta = 2.0 / fma(v0, v0, sigma);
+            const double vi = (row == k + 1) ? v0 : ((row > k + 1) ? xi : 0.0);
+            if (row == k + 1) vsp[row] = v0;
+            if (row < DP) refl[(size_t)k * DP + row] = vi;
+            if (tid == 0) { s_off[k] = alpha; s_beta[k] = beta; }
+            const bool warp_active = (warp * 32 + 31 > k);
+            double p = 0.0;
+            if (warp_active) {
+                double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                for (int j0 = ((D - 1) & ~3); j0 >= 0; j0 -= 4) {
+                    if (j0 + 3 <= k) break;
+                    const double2 xa = *reinterpret_cast<const double2*>(xsp + j0);
+                    const double2 xb = *reinterpret_cast<const double2*>(xsp + j0 + 2);
+                    if (j0 < D) acc[0] = fma(a[j0 < D ? j0 : 0], xa.x, acc[0]);
+                    if (j0 + 1 < D) acc[1] = fma(a[j0 + 1 < D ? j0 + 1 : 0], xa.y, acc[1]);
+                    if (j0 + 2 < D) acc[2] = fma(a[j0 + 2 < D ? j0 + 2 : 0], xb.x, acc[2]);
+                    if (j0 + 3 < D) acc[3] = fma(a[j0 + 3 < D ? j0 + 3 : 0], xb.y, acc[3]);
+                }
+                // the reflector differs from the raw column only in entry k+1 (v0 = x0 - alpha)
+                p = beta * (((acc[0] + acc[1]) + (acc[2] + acc[3])) - alpha * y);
+                if (!(row > k && row < d)) p = 0.0;
+            }
+            if (row < DP) psp[row] = p;
+            {
+                double vp = warp_sum(vi * p);
+                if (lane == 0) redp[8 + warp] = vp;
+            }
+            __syncthreads();                             // #2
+            double vp = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) vp += redp[8 + w];
+            const double kk = 0.5 * beta * vp;
+            // A -= v w^T + w v^T with w = p - kk v  ==>  A_ij -= v_i p_j + (p_i - 2 kk v_i) v_j
+            const double a2 = fma(-2.0 * kk, vi, p);
+            if (warp_active) {
+#pragma unroll
+                for (int j0 = ((D - 1) & ~3); j0 >= 0; j0 -= 4) {
+                    if (j0 + 3 <= k) break;
+                    const double2 pa = *reinterpret_cast<const double2*>(psp + j0);
+                    const double2 pb = *reinterpret_cast<const double2*>(psp + j0 + 2);
+                    const double2 va = *reinterpret_cast<const double2*>(vsp + j0);
+                    const double2 vb = *reinterpret_cast<const double2*>(vsp + j0 + 2);
+                    if (j0 < D) a[j0 < D ? j0 : 0] = fma(-vi, pa.x, fma(-a2, va.x, a[j0 < D ? j0 : 0]));
+                    if (j0 + 1 < D) a[j0 + 1 < D ? j0 + 1 : 0] = fma(-vi, pa.y, fma(-a2, va.y, a[j0 + 1 < D ? j0 + 1 : 0]));
+                    if (j0 + 2 < D) a[j0 + 2 < D ? j0 + 2 : 0] = fma(-vi, pb.x, fma(-a2, vb.x, a[j0 + 2 < D ? j0 + 2 : 0]));
+                    if (j0 + 3 < D) a[j0 + 3 < D ? j0 + 3 : 0] = fma(-vi, pb.y, fma(-a2, vb.y, a[j0 + 3 < D ? j0 + 3 : 0]));
+                }
+            }
+        }
+        // last 2 x 2 block
+        if (d >= 2) {
+            double x, y;
+            pick2<D>(a, d - 2, x, y);
+            if (row == d - 2) s_diag[d - 2] = x;
+            if (row == d - 1) { s_off[d - 2] = x; s_diag[d - 1] = y; s_off[d - 1] = 0.0; }
+        } else if (row == 0) {
+            s_diag[0] = a[0]; s_off[0] = 0.0;
+        }
+        __syncthreads();
+        if (row < d) {
+            a_.bs.tri_d[(size_t)b * d + row] = s_diag[row];
+            a_.bs.tri_e[(size_t)b * d + row] = s_off[row];
+        }
+
+        // ---- Q = H_0 H_1 ... H_{d-3}: my row, accumulated forward (no barrier: reflectors are all in shared memory)
+#pragma unroll
+        for (int j = 0; j < D; ++j) a[j] = (j == row) ? 1.0 : 0.0;
+        for (int k = 0; k < d - 2; ++k) {
+            const double beta = s_beta[k];
+            if (beta == 0.0) continue;
+            const double* r = refl + (size_t)k * DP;
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int j0 = ((D - 1) & ~3); j0 >= 0; j0 -= 4) {
+                if (j0 + 3 <= k) break;
+                const double2 ra = *reinterpret_cast<const double2*>(r + j0);
+                const double2 rb = *reinterpret_cast<const double2*>(r + j0 + 2);
+                if (j0 < D) acc[0] = fma(a[j0 < D ? j0 : 0], ra.x, acc[0]);
+                if (j0 + 1 < D) acc[1] = fma(a[j0 + 1 < D ? j0 + 1 : 0], ra.y, acc[1]);
+                if (j0 + 2 < D) acc[2] = fma(a[j0 + 2 < D ? j0 + 2 : 0], rb.x, acc[2]);
+                if (j0 + 3 < D) acc[3] = fma(a[j0 + 3 < D ? j0 + 3 : 0], rb.y, acc[3]);
+            }
+            const double u = beta * ((acc[0] + acc[1]) + (acc[2] + acc[3]));
+#pragma unroll
+            for (int j0 = ((D - 1) & ~3); j0 >= 0; j0 -= 4) {
+                if (j0 + 3 <= k) break;
+                const double2 ra = *reinterpret_cast<const double2*>(r + j0);
+                const double2 rb = *reinterpret_cast<const double2*>(r + j0 + 2);
+                if (j0 < D) a[j0 < D ? j0 : 0] = fma(-u, ra.x, a[j0 < D ? j0 : 0]);
+                if (j0 + 1 < D) a[j0 + 1 < D ? j0 + 1 : 0] = fma(-u, ra.y, a[j0 + 1 < D ? j0 + 1 : 0]);
+                if (j0 + 2 < D) a[j0 + 2 < D ? j0 + 2 : 0] = fma(-u, rb.x, a[j0 + 2 < D ? j0 + 2 : 0]);
+                if (j0 + 3 < D) a[j0 + 3 < D ? j0 + 3 : 0] = fma(-u, rb.y, a[j0 + 3 < D ? j0 + 3 : 0]);
+            }
+        }
+        // column-major store: for a fixed column the lanes write consecutive rows
+        if (row < d) {
+            double* q = a_.bs.qmat + (size_t)b * d * d + row;
+#pragma unroll
+            for (int j = 0; j < D; ++j)
+                if (j < d) q[(size_t)j * d] = a[j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Replay + evolution + gradient, rows of V in registers
+// ------------------------------------------------------------------------------------------------
+template <int D, int NW>
+struct RpLayout {
+    static constexpr int NT = NW * 32;
+    static constexpr int DP = (D + 1) & ~1;
+    static constexpr int LDV = D | 1;
+    static constexpr int NP = D * (D - 1) / 2;
+    // always live (doubles)
+    static constexpr int VEC = 0;                            // [8][DP]  e, c, fr, fi, ar, ai, br, bi
+    static constexpr int WV = VEC + 8 * DP;                  // double2 [NT]   n_site conj(psi(t*))
+    static constexpr int RED = WV + 2 * NT;                  // [64]
+    static constexpr int PHASED = RED + 64;
+    // replay phase
+    static constexpr int RING = 0;                           // double2 [kRingR][DP]   (c, s) by plane index
+    static constexpr int R1 = kRingR * DP * 2;               // followed by uint2 hdr[maxr] (runtime size)
+    // evolution phase
+    static constexpr int ZT = 0;                             // double2 [kTC][DP]
+    static constexpr int PART = ZT + kTC * DP * 2;           // [kTC][NT + 1]
+    static constexpr int R2 = PART + kTC * (NT + 1);
+    // gradient phase
+    static constexpr int VSM = 0;                            // [D][LDV], then S: [DP diag][NP pairs]
+    static constexpr int R3a = D * LDV;
+    static constexpr int R3b = DP + ((NP + 1) & ~1);
+    static constexpr int R3 = R3a > R3b ? R3a : R3b;
+    static constexpr int R23 = R2 > R3 ? R2 : R3;
+};
+
+template <int D, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) replay_reg_kernel(RegArgs a) {
+    using L = RpLayout<D, NW>;
+    constexpr int NT = L::NT, DP = L::DP, LDV = L::LDV, NP = L::NP;
+    extern __shared__ __align__(16) double sm[];
+    const ProblemView& pv = a.pv;
+    const int d = pv.d, f = pv.f, T = pv.T;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row = tid;
+    const bool dense = !pv.tridiag;
+
+    double* vec = sm + L::VEC;
+    double2* wv = reinterpret_cast<double2*>(sm + L::WV);
+    double* red = sm + L::RED;
+    int* ired = reinterpret_cast<int*>(red + 48);
+    double* ph = sm + L::PHASED;
+    double2* ring = reinterpret_cast<double2*>(ph + L::RING);
+    uint2* hs = reinterpret_cast<uint2*>(ph + L::R1);
+    double2* zt = reinterpret_cast<double2*>(ph + L::ZT);
+    double* part = ph + L::PART;
+    double* vsm = ph + L::VSM;
+    double* sp = ph + L::VSM;
+    // tr[T] sits behind the largest phase region (runtime offset handed in through the launch: bs.maxr bounds hs)
+    const int r1 = L::R1 + 2 * a.bs.maxr;
+    const int phased = (r1 > L::R23 ? r1 : L::R23);
+    double* tr = ph + ((phased + 1) & ~1);
+
+    const double wsite = (row < d) ? pv.occ[row * f + a.site] : 0.0;
+    const double dt = (T > 1) ? pv.tgrid[1] : 0.0;
+
+    for (long long b = blockIdx.x; b < a.n; b += gridDim.x) {
+        const long long batch = b >> 5;
+        const int blane = (int)(b & 31);
+        const int nr_all = a.bs.nrounds[batch];
+        const double2* rec = a.bs.stream + (size_t)batch * a.bs.capit * 32 + blane;
+        const unsigned* hdr = a.bs.hdr + (size_t)batch * a.bs.maxr * 32 + blane;
+        const int* it0s = a.bs.it0 + (size_t)batch * a.bs.maxr;
+        __syncthreads();                                 // previous point is done with every shared region
+        if (tid == 0) ired[0] = 0;
+        // ---- V <- I or Q (column-major: coalesced over the rows)
+        double v[D];
+        if (dense && row < d) {
+            const double* q = a.bs.qmat + (size_t)b * d * d + row;
+#pragma unroll
+            for (int j = 0; j < D; ++j) v[j] = (j < d) ? q[(size_t)j * d] : 0.0;
+        } else {
+#pragma unroll
+            for (int j = 0; j < D; ++j) v[j] = (j == row) ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        // ---- headers of my point; rounds after my point's last active one are skipped
+        {
+            int last = 0;
+            for (int r = tid; r < nr_all; r += NT) {
+                const unsigned h = hdr[(size_t)r * 32];
+                hs[r] = make_uint2(h, (unsigned)it0s[r]);
+                if ((h & 0xff) != 0xff) last = r + 1;
+            }
+            last = __reduce_max_sync(0xffffffffu, last);
+            if (lane == 0 && last > 0) atomicMax(&ired[0], last);
+        }
+        __syncthreads();
+        const int nr = ired[0];
+        // ---- replay.  Ring slot = (c, s) indexed by PLANE; every plane entry is rewritten for every round
+        // (identity outside the round's window), so plane groups may overhang the window on both sides.
+        auto issue = [&](int r) {
+            if (r < nr && tid < D - 1) {
+                const uint2 h = hs[r];
+                const int lp = h.x & 0xff, mtop = (h.x >> 8) & 0xff;
+                double2* dst = ring + (r % kRingR) * DP + tid;
+                if (lp != 0xff && tid >= lp && tid < mtop) cp_async16(dst, rec + (size_t)((int)h.y + (mtop - 1 - tid)) * 32);
+                else *dst = make_double2(1.0, 0.0);
+            }
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int r = 0; r < kRingR - 1; ++r) issue(r);
+        for (int r = 0; r < nr; ++r) {
+            cp_async_wait<kRingR - 2>();                 // my copies of round r have landed
+            __syncthreads();                             // ... and everyone else's; round r-1 is fully consumed
+            issue(r + kRingR - 1);
+            const uint2 h = hs[r];
+            const int lp = h.x & 0xff, mtop = (h.x >> 8) & 0xff;
+            if (lp == 0xff) continue;
+            const double2* cs = ring + (r % kRingR) * DP;
+#pragma unroll
+            for (int i0 = D - 2; i0 >= 0; i0 -= 4) {
+                if (i0 < lp) break;
+                if (i0 - 3 >= mtop) continue;
+                double2 c4[4];
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) c4[k4] = cs[(i0 - k4) >= 0 ? (i0 - k4) : 0];
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const int i = i0 - k4;
+                    if (i >= 0) {
+                        const double x = v[i >= 0 ? i : 0], y = v[i >= 0 ? i + 1 : 1];
+                        const double t1 = c4[k4].x * x, t2 = c4[k4].y * x;
+                        v[i >= 0 ? i : 0] = fma(-c4[k4].y, y, t1);
+                        v[i >= 0 ? i + 1 : 1] = fma(c4[k4].x, y, t2);
+                    }
+                }
+            }
+        }
+        cp_async_wait<0>();
+        __syncthreads();                                 // replay region is dead from here on
+
+        // ---- c = V[0,:], eigenvalues, unit phase steps
+        if (row == 0) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) vec[DP + i] = v[i];
+        }
+        __syncthreads();
+        double ei = 0.0, ci = 0.0, wre = 1.0, wim = 0.0, zr = 0.0, zi = 0.0;
+        if (row < D) {
+            ci = (row < d) ? vec[DP + row] : 0.0;
+            ei = (row < d) ? a.bs.ev[(size_t)b * d + row] : 0.0;
+            const double th = ei * dt;
+            const double lo = fma(ei, dt, -th);          // exact product tail
+            double sn, cs_;
+            sincos(th, &sn, &cs_);
+            wre = fma(-sn, lo, cs_);                     // exp(-i (th + lo))
+            wim = -fma(cs_, lo, sn);
+            zr = ci;
+        }
+        // ---- time evolution in chunks of kTC samples
+        for (int k0 = 0; k0 < T; k0 += kTC) {
+            if (row < D) {
+#pragma unroll 4
+                for (int kk = 0; kk < kTC; ++kk) {
+                    zt[kk * DP + row] = make_double2(zr, zi);
+                    const double nr_ = fma(zr, wre, -(zi * wim));
+                    zi = fma(zr, wim, zi * wre);
+                    zr = nr_;
+                }
+            }
+            __syncthreads();
+            const int kend = (T - k0 < kTC) ? (T - k0) : kTC;
+#pragma unroll 1
+            for (int kk = 0; kk < kend; kk += 2) {
+                const double2* z0 = zt + kk * DP;
+                const double2* z1 = z0 + DP;
+                double pr0 = 0.0, pi0 = 0.0, pr1 = 0.0, pi1 = 0.0;
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    const double2 za = z0[i], zb = z1[i];
+                    pr0 = fma(v[i], za.x, pr0); pi0 = fma(v[i], za.y, pi0);
+                    pr1 = fma(v[i], zb.x, pr1); pi1 = fma(v[i], zb.y, pi1);
+                }
+                part[kk * (NT + 1) + row] = wsite * fma(pr0, pr0, pi0 * pi0);
+                part[(kk + 1) * (NT + 1) + row] = wsite * fma(pr1, pr1, pi1 * pi1);
+            }
+            __syncthreads();
+            if (tid < kTC && k0 + tid < T) {
+                const double* pp = part + tid * (NT + 1);
+                double s0 = 0.0, s1 = 0.0;
+                int j = 0;
+                for (; j + 2 <= d; j += 2) { s0 += pp[j]; s1 += pp[j + 1]; }
+                if (j < d) s0 += pp[j];
+                tr[k0 + tid] = s0 + s1;
+            }
+        }
+        __syncthreads();
+        if (a.trace != nullptr)
+            for (int k = tid; k < T; k += NT) a.trace[b * T + k] = tr[k];
+        if (warp == 0) {
+            int best = -1;
+            double bv = 0.0;
+            for (int k = lane; k < T; k += 32) {
+                const double key = a.acceptor ? tr[k] : -tr[k];
+                if (best < 0 || key > bv) { bv = key; best = k; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+                if (ob >= 0 && (best < 0 || ov > bv || (ov == bv && ob < best))) { bv = ov; best = ob; }
+            }
+            if (lane == 0) {
+                ired[1] = best;
+                if (a.loss) a.loss[b] = a.acceptor ? ((double)pv.N - bv) : -bv;
+                if (a.tstar) a.tstar[b] = best;
+            }
+        }
+        __syncthreads();
+        if (a.grad == nullptr) continue;
+
+        // ---- gradient at t* : f_i = w_i^kbest, z*_i = c_i f_i
+        const int kbest = ired[1];
+        const double ts = pv.tgrid[kbest];
+        double fr = 1.0, fi = 0.0;
+        {
+            double br = wre, bi = wim;
+            for (int e = kbest; e > 0; e >>= 1) {
+                if (e & 1) { const double tt = fma(fr, br, -(fi * bi)); fi = fma(fr, bi, fi * br); fr = tt; }
+                const double t2 = fma(br, br, -(bi * bi)); bi = 2.0 * br * bi; br = t2;
+            }
+        }
+        if (row < D) zt[row] = make_double2(ci * fr, ci * fi);
+        __syncthreads();
+        {
+            double pr0 = 0.0, pi0 = 0.0, pr1 = 0.0, pi1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                const double2 z = zt[i];
+                if (i & 1) { pr1 = fma(v[i], z.x, pr1); pi1 = fma(v[i], z.y, pi1); }
+                else { pr0 = fma(v[i], z.x, pr0); pi0 = fma(v[i], z.y, pi0); }
+            }
+            wv[row] = make_double2(wsite * (pr0 + pr1), -wsite * (pi0 + pi1));
+        }
+        __syncthreads();                                 // zt is dead: V goes to shared memory for the column sums
+        if (row < d) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) vsm[(size_t)row * LDV + i] = v[i];
+        }
+        __syncthreads();
+        if (row < D) {
+            double ar = 0.0, ai = 0.0;
+            if (row < d) {
+                double ar1 = 0.0, ai1 = 0.0;
+                int j = 0;
+                for (; j + 2 <= d; j += 2) {
+                    const double v0 = vsm[(size_t)j * LDV + row], v1 = vsm[(size_t)(j + 1) * LDV + row];
+                    const double2 w0 = wv[j], w1 = wv[j + 1];
+                    ar = fma(v0, w0.x, ar); ai = fma(v0, w0.y, ai);
+                    ar1 = fma(v1, w1.x, ar1); ai1 = fma(v1, w1.y, ai1);
+                }
+                if (j < d) { const double v0 = vsm[(size_t)j * LDV + row]; const double2 w0 = wv[j]; ar = fma(v0, w0.x, ar); ai = fma(v0, w0.y, ai); }
+                ar += ar1; ai += ai1;
+            }
+            const double bre = fma(ar, fr, -(ai * fi)), bim = fma(ar, fi, ai * fr);
+            vec[0 * DP + row] = ei; vec[1 * DP + row] = ci; vec[2 * DP + row] = fr; vec[3 * DP + row] = fi;
+            vec[4 * DP + row] = ar; vec[5 * DP + row] = ai; vec[6 * DP + row] = bre; vec[7 * DP + row] = bim;
+        }
+        __syncthreads();                                 // V in shared memory is dead: the kernel S takes its place
+        if (row < D) sp[row] = (row < d) ? ci * ts * vec[7 * DP + row] : 0.0;      // K_ii = c_i t* Im(b_i)
+        // S_ij = K_ij + K_ji for i < j
+        for (int q0 = tid; q0 < NP; q0 += 2 * NT) {
+            int pi_[2], pj_[2];
+            double dl[2], kd[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int qq = q0 + u * NT;
+                const unsigned ij = a.pair_tab[(qq < NP) ? qq : 0];
+                pi_[u] = ij & 0xff; pj_[u] = ij >> 8;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int i = pi_[u], j = pj_[u];
+                dl[u] = vec[i] - vec[j];
+                const double kij = vec[DP + j] * (vec[6 * DP + i] - vec[4 * DP + i] * vec[2 * DP + j] + vec[5 * DP + i] * vec[3 * DP + j]);
+                const double kji = vec[DP + i] * (vec[6 * DP + j] - vec[4 * DP + j] * vec[2 * DP + i] + vec[5 * DP + j] * vec[3 * DP + i]);
+                kd[u] = kij - kji;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) kd[u] *= fast_rcp(dl[u]);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int qq = q0 + u * NT;
+                if (qq < NP) {
+                    const int i = pi_[u], j = pj_[u];
+                    double sij = kd[u];
+                    if (j >= d) sij = 0.0;
+                    else if (fabs(dl[u] * ts) < 1e-2) {
+                        // near-degenerate: Phi_ij = ts f_j (exp(-i x) - 1)/x ; S = Re[(a_i c_j + a_j c_i) Phi_ij]
+                        double gr, gi;
+                        expm1_over_x(dl[u] * ts, gr, gi);
+                        const double fjr = vec[2 * DP + j], fji = vec[3 * DP + j];
+                        const double phr = ts * (fjr * gr - fji * gi), phi = ts * (fjr * gi + fji * gr);
+                        const double c_i = vec[DP + i], c_j = vec[DP + j];
+                        const double mr = vec[4 * DP + i] * c_j + vec[4 * DP + j] * c_i;
+                        const double mi = vec[5 * DP + i] * c_j + vec[5 * DP + j] * c_i;
+                        sij = mr * phr - mi * phi;
+                    }
+                    sp[DP + qq] = sij;
+                }
+            }
+        }
+        __syncthreads();
+        // G_row = 2 [sum_i K_ii V_i^2 + sum_{i<j} S_ij V_i V_j], every index static
+        double Gm = 0.0;
+        {
+            const double2* sp2 = reinterpret_cast<const double2*>(sp + DP);
+            double2 cur = make_double2(0.0, 0.0);
+            static_for<D>([&](auto Ic) {
+                constexpr int i = decltype(Ic)::value;
+                double acc0 = sp[i] * v[i], acc1 = 0.0;
+                static_for<D - 1 - i>([&](auto Jc) {
+                    constexpr int j = i + 1 + decltype(Jc)::value;
+                    constexpr int qq = i * D - (i * (i + 1)) / 2 + (j - i - 1);
+                    double sv;
+                    if constexpr ((qq & 1) == 0) { cur = sp2[qq >> 1]; sv = cur.x; } else sv = cur.y;
+                    if constexpr (((j - i) & 1) != 0) acc0 = fma(sv, v[j], acc0); else acc1 = fma(sv, v[j], acc1);
+                });
+                Gm = fma(v[i], acc0 + acc1, Gm);
+            });
+        }
+        for (int k = 0; k < f; ++k) {
+            const double qk = (row < d) ? pv.quad[row * f + k] : 0.0;
+            const double s = cta_sum<NW>(qk * (2.0 * Gm), red + (k & 1) * 8, lane, warp);
+            if (tid == 0) a.grad[b * f + k] = a.acceptor ? -s : s;
+        }
+    }
+}
+
+template <int D, int NW, int MINB>
+size_t replay_smem_bytes(int maxr, int T) {
+    using L = RpLayout<D, NW>;
+    const int r1 = L::R1 + 2 * maxr;
+    const int phased = (r1 > L::R23 ? r1 : L::R23);
+    return (size_t)(L::PHASED + ((phased + 1) & ~1) + ((T + 1) & ~1)) * sizeof(double);
+}
+
+template <int D, int NW, int MINB>
+int launch_replay_t(const RegArgs& a, int sms, cudaStream_t st) {
+    const size_t smem = replay_smem_bytes<D, NW, MINB>(a.bs.maxr, a.pv.T);
+    auto kern = replay_reg_kernel<D, NW, MINB>;
+    QTET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QTET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    int per_sm = 0;
+    QTET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)sms * per_sm;
+    if (grid > a.n) grid = a.n;
+    kern<<<(unsigned)grid, NW * 32, smem, st>>>(a);
+    count_launch();
+    QTET_CUDA(cudaGetLastError());
+    return QTET_OK;
+}
+
+template <int D, int NW, int MINB>
+int launch_hh_t(const RegArgs& a, int sms, cudaStream_t st) {
+    const size_t smem = (size_t)HhLayout<D>::TOTAL * sizeof(double);
+    auto kern = hh_reg_kernel<D, NW, MINB>;
+    QTET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QTET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    int per_sm = 0;
+    QTET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)sms * per_sm;
+    if (grid > a.n) grid = a.n;
+    kern<<<(unsigned)grid, NW * 32, smem, st>>>(a);
+    count_launch();
+    QTET_CUDA(cudaGetLastError());
+    return QTET_OK;
+}
+
+}  // namespace
+
+// Padded dimension of the register-resident kernels for Fock dimension d, or 0 when d is out of their range.
+int bigreg_padded_dim(int d) {
+    const int sizes[] = {16, 32, 48, 66, 84, 101};
+    for (int s : sizes) if (d <= s) return s;
+    return 0;
+}
+
+int bigreg_max_timesteps() { return 2048; }
+
+static RegArgs make_args(const ProblemView& pv, const double* chis, int64_t n, int site, const BigStream& bs,
+                         const unsigned short* pair_tab, double* loss, double* grad, int32_t* tstar, double* trace) {
+    RegArgs a;
+    a.pv = pv; a.chis = chis; a.n = n; a.site = site; a.acceptor = (site == pv.f - 1) ? 1 : 0; a.bs = bs;
+    a.pair_tab = pair_tab; a.loss = loss; a.grad = grad; a.tstar = tstar; a.trace = trace;
+    return a;
+}
+
+int launch_hh_reg(const ProblemView& pv, const double* chis, int64_t n, const BigStream& bs, int sms, cudaStream_t st) {
+    const RegArgs a = make_args(pv, chis, n, 0, bs, nullptr, nullptr, nullptr, nullptr, nullptr);
+    switch (bigreg_padded_dim(pv.d)) {
+        case 16: return launch_hh_t<16, 1, 8>(a, sms, st);
+        case 32: return launch_hh_t<32, 1, 8>(a, sms, st);
+        case 48: return launch_hh_t<48, 2, 4>(a, sms, st);
+        case 66: return launch_hh_t<66, 3, 4>(a, sms, st);
+        case 84: return launch_hh_t<84, 3, 2>(a, sms, st);
+        case 101: return launch_hh_t<101, 4, 2>(a, sms, st);
+        default: break;
+    }
+    set_error("register-resident Householder kernel: dimension out of range");
+    return QTET_EUNSUPPORTED;
+}
+
+int launch_replay_reg(const ProblemView& pv, const double* chis, int64_t n, int site, const BigStream& bs,
+                      const unsigned short* pair_tab, double* loss, double* grad, int32_t* tstar, double* trace, int sms,
+                      cudaStream_t st) {
+    const RegArgs a = make_args(pv, chis, n, site, bs, pair_tab, loss, grad, tstar, trace);
+    switch (bigreg_padded_dim(pv.d)) {
+        case 16: return launch_replay_t<16, 1, 8>(a, sms, st);
+        case 32: return launch_replay_t<32, 1, 8>(a, sms, st);
+        case 48: return launch_replay_t<48, 2, 4>(a, sms, st);
+        case 66: return launch_replay_t<66, 3, 4>(a, sms, st);
+        case 84: return launch_replay_t<84, 3, 2>(a, sms, st);
+        case 101: return launch_replay_t<101, 4, 2>(a, sms, st);
+        default: break;
+    }
+    set_error("register-resident replay kernel: dimension out of range");
+    return QTET_EUNSUPPORTED;
+}
+
+}  // namespace qtet
