@@ -186,7 +186,8 @@ __global__ void __launch_bounds__(kWarpsBig * 32) ql_scalar_big_kernel(BigQlArgs
                 overflow = true;
                 break;
             }
-            hdr[(size_t)round * 32] = (unsigned)(done ? 0xff : l) | ((unsigned)mtop << 8) | ((unsigned)lbot << 16);
+            // l (0xff = idle) | mtop << 8 (batch-uniform top of the round's rows) | lbot << 16 | my own block top m << 24
+            hdr[(size_t)round * 32] = (unsigned)(done ? 0xff : l) | ((unsigned)mtop << 8) | ((unsigned)lbot << 16) | ((unsigned)m << 24);
             if (lane == 0) it0s[round] = it;
             double g = 0.0, s = 1.0, c = 1.0, pp = 0.0, dnext = 0.0;
             if (!done) {

@@ -8,7 +8,7 @@ namespace qtet {
 struct BigStream {
     // written by the scalar QL kernel, read by the replay
     double2* stream = nullptr;     // [nb][capit][32]  one 512 B row per plane of a round: (c, s) per lane
-    unsigned* hdr = nullptr;       // [nb][maxr][32]   l (0xff = idle) | mtop << 8 | lbot << 16
+    unsigned* hdr = nullptr;       // [nb][maxr][32]   l (0xff = idle) | mtop << 8 | lbot << 16 | m << 24 (the lane's own block top)
     int* it0 = nullptr;            // [nb][maxr]       first stream row of the round
     int* nrounds = nullptr;        // [nb]
     double* ev = nullptr;          // [n][d]           eigenvalues (shifted by the mean of the diagonal)

@@ -24,7 +24,11 @@ namespace qtet {
 
 namespace {
 
-constexpr int kRingR = 4;      // rounds of (c, s) in flight per CTA (cp.async ring)
+constexpr int kRingR = 4;      // trips of (c, s) in flight per CTA (cp.async ring)
+#ifndef QTET_FUSE
+#define QTET_FUSE 2
+#endif
+constexpr int kFuse = QTET_FUSE;   // QL rounds replayed together per trip
 constexpr int kTC = 16;        // time samples per evolution chunk
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -35,6 +39,19 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Shared-memory address as an opaque 32-bit register: the compiler otherwise rematerialises the window base
+// (S2UR SR_CgaCtaId + ULEA, ~25 cycles of scoreboard stall) in every basic block of an unrolled, branchy sweep.
+__device__ __forceinline__ unsigned smem_addr(const void* p) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));
+    return a;
+}
+__device__ __forceinline__ double2 lds128(unsigned addr) {
+    double2 r;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(addr));
+    return r;
+}
+
 __device__ __forceinline__ double fast_rcp(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
@@ -42,6 +59,15 @@ __device__ __forceinline__ double fast_rcp(double x) {
     r = fma(fma(-x, r, 1.0), r, r);
     return r;
 }
+
+#ifdef QTET_PHASE_TIMING
+__device__ unsigned long long g_big_phase_cycles[16];
+#define BPHASE_START() long long _t0 = clock64()
+#define BPHASE_MARK(idx) do { const long long _t = clock64(); if (tid == 0) atomicAdd(&g_big_phase_cycles[idx], (unsigned long long)(_t - _t0)); _t0 = _t; } while (0)
+#else
+#define BPHASE_START() do {} while (0)
+#define BPHASE_MARK(idx) do {} while (0)
+#endif
 
 struct RegArgs {
     ProblemView pv;
@@ -95,7 +121,7 @@ __device__ __forceinline__ double cta_sum(double v, double* red, int lane, int w
 // ------------------------------------------------------------------------------------------------
 template <int D>
 struct HhLayout {
-    static constexpr int DP = (D + 3) & ~3;
+    static constexpr int DP = (D + 7) & ~7;
     // doubles
     static constexpr int XS = 0;                   // [2][DP]  raw column below the diagonal (zeros above)
     static constexpr int VS = XS + 2 * DP;         // [2][DP]  reflector
@@ -125,10 +151,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) hh_reg_kernel(RegArgs a_) {
     double* s_beta = sm + L::BETA;
     double* red = sm + L::RED;
     double* refl = sm + L::REFL;
+    constexpr int NG8 = DP / 8;                    // column groups of 8
+    const unsigned xs_a = smem_addr(xs), vs_a = smem_addr(vs), ps_a = smem_addr(ps), refl_a = smem_addr(refl);
 
     for (long long b = blockIdx.x; b < a_.n; b += gridDim.x) {
         const double* chi = a_.chis + b * f;
         __syncthreads();
+        BPHASE_START();
         // ---- my row of H: hopping part (symmetric, so column `row` read coalesced) + diagonal
         double a[D];
         {
@@ -145,6 +174,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) hh_reg_kernel(RegArgs a_) {
         }
         if (row < DP) { xs[row] = 0.0; xs[DP + row] = 0.0; vs[row] = 0.0; vs[DP + row] = 0.0; ps[row] = 0.0; ps[DP + row] = 0.0; }
 
+        BPHASE_MARK(0);
         // ---- reduction: two CTA barriers per column
         for (int k = 0; k < d - 2; ++k) {
             const int par = k & 1;
@@ -172,28 +202,35 @@ __global__ void __launch_bounds__(NW * 32, MINB) hh_reg_kernel(RegArgs a_) {
                 if (tid == 0) { s_off[k] = x0; s_beta[k] = 0.0; }
                 continue;
             }
-            const double mu = sqrt(fma(x0, x0, sigma));
-            const double alpha = (x0 >= 0.0) ? -mu : mu;
+            const double nrm2 = fma(x0, x0, sigma);
+            const double mu = nrm2 * rsqrt(nrm2);          // a few ulp off sqrt: only moves the tridiagonal entry by that much;
+            const double alpha = (x0 >= 0.0) ? -mu : mu;   // H stays orthogonal because beta is formed from the v actually used
             const double v0 = x0 - alpha;
-            const double beta = 2.0 / fma(v0, v0, sigma);
+            const double beta = 2.0 * fast_rcp(fma(v0, v0, sigma));
             const double vi = (row == k + 1) ? v0 : ((row > k + 1) ? xi : 0.0);
             if (row == k + 1) vsp[row] = v0;
             if (row < DP) refl[(size_t)k * DP + row] = vi;
             if (tid == 0) { s_off[k] = alpha; s_beta[k] = beta; }
             const bool warp_active = (warp * 32 + 31 > k);
+            const unsigned xa_ = xs_a + par * (DP * 8), va_ = vs_a + par * (DP * 8), pa_ = ps_a + par * (DP * 8);
             double p = 0.0;
             if (warp_active) {
                 double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                bool live = true;
+                static_for<NG8>([&](auto Gc) {
+                    constexpr int j0 = (NG8 - 1 - decltype(Gc)::value) * 8;
+                    if (live && j0 + 7 <= k) live = false;
+                    if (live) {
 #pragma unroll
-                for (int j0 = ((D - 1) & ~3); j0 >= 0; j0 -= 4) {
-                    if (j0 + 3 <= k) break;
-                    const double2 xa = *reinterpret_cast<const double2*>(xsp + j0);
-                    const double2 xb = *reinterpret_cast<const double2*>(xsp + j0 + 2);
-                    if (j0 < D) acc[0] = fma(a[j0 < D ? j0 : 0], xa.x, acc[0]);
-                    if (j0 + 1 < D) acc[1] = fma(a[j0 + 1 < D ? j0 + 1 : 0], xa.y, acc[1]);
-                    if (j0 + 2 < D) acc[2] = fma(a[j0 + 2 < D ? j0 + 2 : 0], xb.x, acc[2]);
-                    if (j0 + 3 < D) acc[3] = fma(a[j0 + 3 < D ? j0 + 3 : 0], xb.y, acc[3]);
-                }
+                        for (int u = 0; u < 8; u += 2) {
+                            if (j0 + u < D) {
+                                const double2 x2 = lds128(xa_ + (j0 + u) * 8);
+                                acc[u & 3] = fma(a[j0 + u < D ? j0 + u : 0], x2.x, acc[u & 3]);
+                                if (j0 + u + 1 < D) acc[(u + 1) & 3] = fma(a[j0 + u + 1 < D ? j0 + u + 1 : 0], x2.y, acc[(u + 1) & 3]);
+                            }
+                        }
+                    }
+                });
                 // the reflector differs from the raw column only in entry k+1 (v0 = x0 - alpha)
                 p = beta * (((acc[0] + acc[1]) + (acc[2] + acc[3])) - alpha * y);
                 if (!(row > k && row < d)) p = 0.0;
@@ -211,20 +248,27 @@ __global__ void __launch_bounds__(NW * 32, MINB) hh_reg_kernel(RegArgs a_) {
             // A -= v w^T + w v^T with w = p - kk v  ==>  A_ij -= v_i p_j + (p_i - 2 kk v_i) v_j
             const double a2 = fma(-2.0 * kk, vi, p);
             if (warp_active) {
+                bool live = true;
+                static_for<NG8>([&](auto Gc) {
+                    constexpr int j0 = (NG8 - 1 - decltype(Gc)::value) * 8;
+                    if (live && j0 + 7 <= k) live = false;
+                    if (live) {
 #pragma unroll
-                for (int j0 = ((D - 1) & ~3); j0 >= 0; j0 -= 4) {
-                    if (j0 + 3 <= k) break;
-                    const double2 pa = *reinterpret_cast<const double2*>(psp + j0);
-                    const double2 pb = *reinterpret_cast<const double2*>(psp + j0 + 2);
-                    const double2 va = *reinterpret_cast<const double2*>(vsp + j0);
-                    const double2 vb = *reinterpret_cast<const double2*>(vsp + j0 + 2);
-                    if (j0 < D) a[j0 < D ? j0 : 0] = fma(-vi, pa.x, fma(-a2, va.x, a[j0 < D ? j0 : 0]));
-                    if (j0 + 1 < D) a[j0 + 1 < D ? j0 + 1 : 0] = fma(-vi, pa.y, fma(-a2, va.y, a[j0 + 1 < D ? j0 + 1 : 0]));
-                    if (j0 + 2 < D) a[j0 + 2 < D ? j0 + 2 : 0] = fma(-vi, pb.x, fma(-a2, vb.x, a[j0 + 2 < D ? j0 + 2 : 0]));
-                    if (j0 + 3 < D) a[j0 + 3 < D ? j0 + 3 : 0] = fma(-vi, pb.y, fma(-a2, vb.y, a[j0 + 3 < D ? j0 + 3 : 0]));
-                }
+                        for (int u = 0; u < 8; u += 2) {
+                            if (j0 + u < D) {
+                                const double2 p2 = lds128(pa_ + (j0 + u) * 8);
+                                const double2 v2 = lds128(va_ + (j0 + u) * 8);
+                                constexpr int dm = D - 1;
+                                const int c0 = (j0 + u <= dm) ? j0 + u : 0, c1 = (j0 + u + 1 <= dm) ? j0 + u + 1 : 0;
+                                a[c0] = fma(-vi, p2.x, fma(-a2, v2.x, a[c0]));
+                                if (j0 + u + 1 < D) a[c1] = fma(-vi, p2.y, fma(-a2, v2.y, a[c1]));
+                            }
+                        }
+                    }
+                });
             }
         }
+        BPHASE_MARK(1);
         // last 2 x 2 block
         if (d >= 2) {
             double x, y;
@@ -246,30 +290,47 @@ __global__ void __launch_bounds__(NW * 32, MINB) hh_reg_kernel(RegArgs a_) {
         for (int k = 0; k < d - 2; ++k) {
             const double beta = s_beta[k];
             if (beta == 0.0) continue;
-            const double* r = refl + (size_t)k * DP;
+            const unsigned ra_ = refl_a + (unsigned)k * (DP * 8);
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            {
+                bool live = true;
+                static_for<NG8>([&](auto Gc) {
+                    constexpr int j0 = (NG8 - 1 - decltype(Gc)::value) * 8;
+                    if (live && j0 + 7 <= k) live = false;
+                    if (live) {
 #pragma unroll
-            for (int j0 = ((D - 1) & ~3); j0 >= 0; j0 -= 4) {
-                if (j0 + 3 <= k) break;
-                const double2 ra = *reinterpret_cast<const double2*>(r + j0);
-                const double2 rb = *reinterpret_cast<const double2*>(r + j0 + 2);
-                if (j0 < D) acc[0] = fma(a[j0 < D ? j0 : 0], ra.x, acc[0]);
-                if (j0 + 1 < D) acc[1] = fma(a[j0 + 1 < D ? j0 + 1 : 0], ra.y, acc[1]);
-                if (j0 + 2 < D) acc[2] = fma(a[j0 + 2 < D ? j0 + 2 : 0], rb.x, acc[2]);
-                if (j0 + 3 < D) acc[3] = fma(a[j0 + 3 < D ? j0 + 3 : 0], rb.y, acc[3]);
+                        for (int u = 0; u < 8; u += 2) {
+                            if (j0 + u < D) {
+                                const double2 r2 = lds128(ra_ + (j0 + u) * 8);
+                                acc[u & 3] = fma(a[j0 + u < D ? j0 + u : 0], r2.x, acc[u & 3]);
+                                if (j0 + u + 1 < D) acc[(u + 1) & 3] = fma(a[j0 + u + 1 < D ? j0 + u + 1 : 0], r2.y, acc[(u + 1) & 3]);
+                            }
+                        }
+                    }
+                });
             }
-            const double u = beta * ((acc[0] + acc[1]) + (acc[2] + acc[3]));
+            const double u_ = beta * ((acc[0] + acc[1]) + (acc[2] + acc[3]));
+            {
+                bool live = true;
+                static_for<NG8>([&](auto Gc) {
+                    constexpr int j0 = (NG8 - 1 - decltype(Gc)::value) * 8;
+                    if (live && j0 + 7 <= k) live = false;
+                    if (live) {
 #pragma unroll
-            for (int j0 = ((D - 1) & ~3); j0 >= 0; j0 -= 4) {
-                if (j0 + 3 <= k) break;
-                const double2 ra = *reinterpret_cast<const double2*>(r + j0);
-                const double2 rb = *reinterpret_cast<const double2*>(r + j0 + 2);
-                if (j0 < D) a[j0 < D ? j0 : 0] = fma(-u, ra.x, a[j0 < D ? j0 : 0]);
-                if (j0 + 1 < D) a[j0 + 1 < D ? j0 + 1 : 0] = fma(-u, ra.y, a[j0 + 1 < D ? j0 + 1 : 0]);
-                if (j0 + 2 < D) a[j0 + 2 < D ? j0 + 2 : 0] = fma(-u, rb.x, a[j0 + 2 < D ? j0 + 2 : 0]);
-                if (j0 + 3 < D) a[j0 + 3 < D ? j0 + 3 : 0] = fma(-u, rb.y, a[j0 + 3 < D ? j0 + 3 : 0]);
+                        for (int u = 0; u < 8; u += 2) {
+                            if (j0 + u < D) {
+                                const double2 r2 = lds128(ra_ + (j0 + u) * 8);
+                                constexpr int dm = D - 1;
+                                const int c0 = (j0 + u <= dm) ? j0 + u : 0, c1 = (j0 + u + 1 <= dm) ? j0 + u + 1 : 0;
+                                a[c0] = fma(-u_, r2.x, a[c0]);
+                                if (j0 + u + 1 < D) a[c1] = fma(-u_, r2.y, a[c1]);
+                            }
+                        }
+                    }
+                });
             }
         }
+        BPHASE_MARK(2);
         // column-major store: for a fixed column the lanes write consecutive rows
         if (row < d) {
             double* q = a_.bs.qmat + (size_t)b * d * d + row;
@@ -277,6 +338,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) hh_reg_kernel(RegArgs a_) {
             for (int j = 0; j < D; ++j)
                 if (j < d) q[(size_t)j * d] = a[j];
         }
+        BPHASE_MARK(3);
     }
 }
 
@@ -295,8 +357,8 @@ struct RpLayout {
     static constexpr int RED = WV + 2 * NT;                  // [64]
     static constexpr int PHASED = RED + 64;
     // replay phase
-    static constexpr int RING = 0;                           // double2 [kRingR][DP]   (c, s) by plane index
-    static constexpr int R1 = kRingR * DP * 2;               // followed by uint2 hdr[maxr] (runtime size)
+    static constexpr int RING = 0;                           // double2 [kRingR][kFuse][DP]   (c, s) by plane index
+    static constexpr int R1 = kRingR * kFuse * DP * 2;       // followed by uint2 hdr[maxr] (runtime size)
     // evolution phase
     static constexpr int ZT = 0;                             // double2 [kTC][DP]
     static constexpr int PART = ZT + kTC * DP * 2;           // [kTC][NT + 1]
@@ -309,10 +371,11 @@ struct RpLayout {
     static constexpr int R23 = R2 > R3 ? R2 : R3;
 };
 
-template <int D, int NW, int MINB>
+template <int D, int NW, int MINB, int GS>
 __global__ void __launch_bounds__(NW * 32, MINB) replay_reg_kernel(RegArgs a) {
     using L = RpLayout<D, NW>;
     constexpr int NT = L::NT, DP = L::DP, LDV = L::LDV, NP = L::NP;
+    constexpr int NG = (D - 1 + 2 * (kFuse - 1) + GS - 1) / GS;     // plane groups of GS steps per trip
     extern __shared__ __align__(16) double sm[];
     const ProblemView& pv = a.pv;
     const int d = pv.d, f = pv.f, T = pv.T;
@@ -327,6 +390,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) replay_reg_kernel(RegArgs a) {
     double* ph = sm + L::PHASED;
     double2* ring = reinterpret_cast<double2*>(ph + L::RING);
     uint2* hs = reinterpret_cast<uint2*>(ph + L::R1);
+    int2* tw = reinterpret_cast<int2*>(ph + L::R1 + a.bs.maxr);     // per-trip windows, behind the headers
+    const unsigned ring_a = smem_addr(ring);
     double2* zt = reinterpret_cast<double2*>(ph + L::ZT);
     double* part = ph + L::PART;
     double* vsm = ph + L::VSM;
@@ -347,6 +412,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) replay_reg_kernel(RegArgs a) {
         const unsigned* hdr = a.bs.hdr + (size_t)batch * a.bs.maxr * 32 + blane;
         const int* it0s = a.bs.it0 + (size_t)batch * a.bs.maxr;
         __syncthreads();                                 // previous point is done with every shared region
+        BPHASE_START();
         if (tid == 0) ired[0] = 0;
         // ---- V <- I or Q (column-major: coalesced over the rows)
         double v[D];
@@ -372,49 +438,106 @@ __global__ void __launch_bounds__(NW * 32, MINB) replay_reg_kernel(RegArgs a) {
         }
         __syncthreads();
         const int nr = ired[0];
-        // ---- replay.  Ring slot = (c, s) indexed by PLANE; every plane entry is rewritten for every round
-        // (identity outside the round's window), so plane groups may overhang the window on both sides.
-        auto issue = [&](int r) {
-            if (r < nr && tid < D - 1) {
-                const uint2 h = hs[r];
-                const int lp = h.x & 0xff, mtop = (h.x >> 8) & 0xff;
-                double2* dst = ring + (r % kRingR) * DP + tid;
-                if (lp != 0xff && tid >= lp && tid < mtop) cp_async16(dst, rec + (size_t)((int)h.y + (mtop - 1 - tid)) * 32);
-                else *dst = make_double2(1.0, 0.0);
+        BPHASE_MARK(4);
+        // ---- replay.  kFuse consecutive rounds are swept TOGETHER: round f of a trip trails round f-1 by two
+        // planes, so the trip carries kFuse independent dependency chains per row and costs one barrier.  A ring slot
+        // holds the (c, s) of those rounds indexed by PLANE; every plane entry is rewritten for every trip (identity
+        // outside a round's window), so plane groups may overhang the windows on both sides.
+        const int ntrip = (nr + kFuse - 1) / kFuse;
+        // window of every trip in units of the LEADER's plane index (round f works on plane i + 2 f at step i)
+        for (int s_ = tid; s_ < ntrip; s_ += NT) {
+            int ilo = 1 << 20, ihi = -(1 << 20);
+#pragma unroll
+            for (int f_ = 0; f_ < kFuse; ++f_) {
+                const int r = s_ * kFuse + f_;
+                if (r < nr) {
+                    const uint2 h = hs[r];
+                    const int lp = h.x & 0xff, mine = h.x >> 24;     // my point sweeps planes [lp, mine)
+                    if (lp != 0xff) { ilo = min(ilo, lp - 2 * f_); ihi = max(ihi, mine - 1 - 2 * f_); }
+                }
+            }
+            tw[s_] = make_int2(ilo, ihi);
+        }
+        __syncthreads();
+        // (c, s) of trip s_: plane entry `tid` of every fused round, copied global -> shared (identity outside the window)
+        auto issue = [&](int s_, const uint2 (&hh)[kFuse]) {
+            if (s_ < ntrip && tid < D - 1) {
+#pragma unroll
+                for (int f_ = 0; f_ < kFuse; ++f_) {
+                    double2* dst = ring + ((s_ % kRingR) * kFuse + f_) * DP + tid;
+                    const int lp = hh[f_].x & 0xff, mtop = (hh[f_].x >> 8) & 0xff, mine = hh[f_].x >> 24;
+                    if (lp != 0xff && tid >= lp && tid < mine) cp_async16(dst, rec + (size_t)((int)hh[f_].y + (mtop - 1 - tid)) * 32);
+                    else *dst = make_double2(1.0, 0.0);
+                }
             }
             cp_async_commit();
         };
+        auto headers = [&](int s_, uint2 (&hh)[kFuse]) {
 #pragma unroll
-        for (int r = 0; r < kRingR - 1; ++r) issue(r);
-        for (int r = 0; r < nr; ++r) {
-            cp_async_wait<kRingR - 2>();                 // my copies of round r have landed
-            __syncthreads();                             // ... and everyone else's; round r-1 is fully consumed
-            issue(r + kRingR - 1);
-            const uint2 h = hs[r];
-            const int lp = h.x & 0xff, mtop = (h.x >> 8) & 0xff;
-            if (lp == 0xff) continue;
-            const double2* cs = ring + (r % kRingR) * DP;
-#pragma unroll
-            for (int i0 = D - 2; i0 >= 0; i0 -= 4) {
-                if (i0 < lp) break;
-                if (i0 - 3 >= mtop) continue;
-                double2 c4[4];
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) c4[k4] = cs[(i0 - k4) >= 0 ? (i0 - k4) : 0];
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                    const int i = i0 - k4;
-                    if (i >= 0) {
-                        const double x = v[i >= 0 ? i : 0], y = v[i >= 0 ? i + 1 : 1];
-                        const double t1 = c4[k4].x * x, t2 = c4[k4].y * x;
-                        v[i >= 0 ? i : 0] = fma(-c4[k4].y, y, t1);
-                        v[i >= 0 ? i + 1 : 1] = fma(c4[k4].x, y, t2);
-                    }
-                }
+            for (int f_ = 0; f_ < kFuse; ++f_) {
+                const int r = s_ * kFuse + f_;
+                hh[f_] = (r < nr) ? hs[r] : make_uint2(0xffu, 0u);
             }
+        };
+#pragma unroll
+        for (int s_ = 0; s_ < kRingR - 1; ++s_) { uint2 hh[kFuse]; headers(s_, hh); issue(s_, hh); }
+        int2 wnext = (ntrip > 0) ? tw[0] : make_int2(0, -1);
+        for (int s_ = 0; s_ < ntrip; ++s_) {
+            cp_async_wait<kRingR - 2>();                 // my copies of trip s_ have landed
+            __syncthreads();                             // ... and everyone else's; trip s_-1 is fully consumed
+            uint2 hn[kFuse];
+            headers(s_ + kRingR - 1, hn);                // loaded now, used after the sweep
+            const int2 w = wnext;
+            wnext = tw[(s_ + 1 < ntrip) ? s_ + 1 : s_];
+            if (w.y >= w.x) {
+                const int ilo = w.x;
+                const unsigned ca = ring_a + (unsigned)((s_ % kRingR) * kFuse * DP * 16);
+                // plane groups top-down from plane D-2 (the windows always reach the top; identity entries cover the
+                // exceptions), the next group's (c, s) fetched while this one is applied, one uniform exit test per group
+                double2 cur[GS][kFuse], nxt[GS][kFuse];
+                auto fetch = [&](double2 (&dst)[GS][kFuse], auto Gc) {
+                    constexpr int i0 = D - 2 - GS * decltype(Gc)::value;
+#pragma unroll
+                    for (int k4 = 0; k4 < GS; ++k4)
+#pragma unroll
+                        for (int f_ = 0; f_ < kFuse; ++f_) {
+                            const int pl = i0 - k4 + 2 * f_;
+                            if (pl >= 0 && pl <= D - 2) dst[k4][f_] = lds128(ca + (unsigned)((f_ * DP + (pl >= 0 ? pl : 0)) * 16));
+                        }
+                };
+                fetch(cur, std::integral_constant<int, 0>{});
+                bool live = true;
+                static_for<NG>([&](auto Gc) {
+                    constexpr int g_ = decltype(Gc)::value;
+                    constexpr int i0 = D - 2 - GS * g_;
+                    if (live && i0 < ilo) live = false;
+                    if (live) {
+                        if constexpr (g_ + 1 < NG) fetch(nxt, std::integral_constant<int, g_ + 1>{});
+#pragma unroll
+                        for (int k4 = 0; k4 < GS; ++k4)
+#pragma unroll
+                            for (int f_ = 0; f_ < kFuse; ++f_) {
+                                const int pl = i0 - k4 + 2 * f_;
+                                if (pl >= 0 && pl <= D - 2) {
+                                    const int pc = (pl >= 0 && pl <= D - 2) ? pl : 0;
+                                    const double x = v[pc], y = v[pc + 1];
+                                    const double t1 = cur[k4][f_].x * x, t2 = cur[k4][f_].y * x;
+                                    v[pc] = fma(-cur[k4][f_].y, y, t1);
+                                    v[pc + 1] = fma(cur[k4][f_].x, y, t2);
+                                }
+                            }
+#pragma unroll
+                        for (int k4 = 0; k4 < GS; ++k4)
+#pragma unroll
+                            for (int f_ = 0; f_ < kFuse; ++f_) cur[k4][f_] = nxt[k4][f_];
+                    }
+                });
+            }
+            issue(s_ + kRingR - 1, hn);
         }
         cp_async_wait<0>();
         __syncthreads();                                 // replay region is dead from here on
+        BPHASE_MARK(5);
 
         // ---- c = V[0,:], eigenvalues, unit phase steps
         if (row == 0) {
@@ -472,6 +595,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) replay_reg_kernel(RegArgs a) {
             }
         }
         __syncthreads();
+        BPHASE_MARK(6);
         if (a.trace != nullptr)
             for (int k = tid; k < T; k += NT) a.trace[b * T + k] = tr[k];
         if (warp == 0) {
@@ -544,6 +668,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) replay_reg_kernel(RegArgs a) {
             vec[4 * DP + row] = ar; vec[5 * DP + row] = ai; vec[6 * DP + row] = bre; vec[7 * DP + row] = bim;
         }
         __syncthreads();                                 // V in shared memory is dead: the kernel S takes its place
+        BPHASE_MARK(7);
         if (row < D) sp[row] = (row < d) ? ci * ts * vec[7 * DP + row] : 0.0;      // K_ii = c_i t* Im(b_i)
         // S_ij = K_ij + K_ji for i < j
         for (int q0 = tid; q0 < NP; q0 += 2 * NT) {
@@ -588,6 +713,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) replay_reg_kernel(RegArgs a) {
             }
         }
         __syncthreads();
+        BPHASE_MARK(8);
         // G_row = 2 [sum_i K_ii V_i^2 + sum_{i<j} S_ij V_i V_j], every index static
         double Gm = 0.0;
         {
@@ -611,10 +737,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) replay_reg_kernel(RegArgs a) {
             const double s = cta_sum<NW>(qk * (2.0 * Gm), red + (k & 1) * 8, lane, warp);
             if (tid == 0) a.grad[b * f + k] = a.acceptor ? -s : s;
         }
+        BPHASE_MARK(9);
     }
 }
 
-template <int D, int NW, int MINB>
+template <int D, int NW>
 size_t replay_smem_bytes(int maxr, int T) {
     using L = RpLayout<D, NW>;
     const int r1 = L::R1 + 2 * maxr;
@@ -622,10 +749,10 @@ size_t replay_smem_bytes(int maxr, int T) {
     return (size_t)(L::PHASED + ((phased + 1) & ~1) + ((T + 1) & ~1)) * sizeof(double);
 }
 
-template <int D, int NW, int MINB>
+template <int D, int NW, int MINB, int GS>
 int launch_replay_t(const RegArgs& a, int sms, cudaStream_t st) {
-    const size_t smem = replay_smem_bytes<D, NW, MINB>(a.bs.maxr, a.pv.T);
-    auto kern = replay_reg_kernel<D, NW, MINB>;
+    const size_t smem = replay_smem_bytes<D, NW>(a.bs.maxr, a.pv.T);
+    auto kern = replay_reg_kernel<D, NW, MINB, GS>;
     QTET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     QTET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int per_sm = 0;
@@ -657,6 +784,14 @@ int launch_hh_t(const RegArgs& a, int sms, cudaStream_t st) {
 }
 
 }  // namespace
+
+#ifdef QTET_PHASE_TIMING
+extern "C" void qtet_debug_big_phase_cycles(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_big_phase_cycles, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_big_phase_cycles, z, sizeof(z)); }
+}
+#endif
 
 // Padded dimension of the register-resident kernels for Fock dimension d, or 0 when d is out of their range.
 int bigreg_padded_dim(int d) {
@@ -695,12 +830,12 @@ int launch_replay_reg(const ProblemView& pv, const double* chis, int64_t n, int 
                       cudaStream_t st) {
     const RegArgs a = make_args(pv, chis, n, site, bs, pair_tab, loss, grad, tstar, trace);
     switch (bigreg_padded_dim(pv.d)) {
-        case 16: return launch_replay_t<16, 1, 8>(a, sms, st);
-        case 32: return launch_replay_t<32, 1, 8>(a, sms, st);
-        case 48: return launch_replay_t<48, 2, 4>(a, sms, st);
-        case 66: return launch_replay_t<66, 3, 4>(a, sms, st);
-        case 84: return launch_replay_t<84, 3, 2>(a, sms, st);
-        case 101: return launch_replay_t<101, 4, 2>(a, sms, st);
+        case 16: return launch_replay_t<16, 1, 8, 4>(a, sms, st);
+        case 32: return launch_replay_t<32, 1, 8, 4>(a, sms, st);
+        case 48: return launch_replay_t<48, 2, 4, 4>(a, sms, st);
+        case 66: return launch_replay_t<66, 3, 3, 4>(a, sms, st);
+        case 84: return launch_replay_t<84, 3, 2, 4>(a, sms, st);
+        case 101: return launch_replay_t<101, 4, 2, 2>(a, sms, st);
         default: break;
     }
     set_error("register-resident replay kernel: dimension out of range");
