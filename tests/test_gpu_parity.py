@@ -91,6 +91,67 @@ def test_chain_loss_grad_vs_oracle(native, O, N, omegas):
         _compare(native, O, make_const(N, omegas), X, site, loss_atol=2e-10, grad_rtol=5e-8)
 
 
+@pytest.mark.parametrize("N,omegas", [
+    (33, (-3, 3)),          # d = 34  -> register kernels padded to 48
+    (50, (-3, 3)),          # d = 51  -> 66
+    (70, (-3, 3)),          # d = 71  -> 84
+    (90, (-3, 3)),          # d = 91  -> 101
+    (3, (-3, 3, 3)),        # d = 10  -> 16, dense (Householder in registers)
+    (6, (-3, 3, 3)),        # d = 28  -> 32, dense
+    (8, (-3, 1, 3)),        # d = 45  -> 48, dense
+    (5, (-3, 0, 1, 3)),     # d = 56  -> 66, dense 4-site chain
+    (6, (-3, 0, 1, 3)),     # d = 84  -> 84, dense
+    (12, (-3, 3, 3)),       # d = 91  -> 101, dense
+])
+def test_register_resident_large_d_kernels(native, O, N, omegas):
+    """Every padded size of the register-resident large-d kernels (qtet_bigreg.cu), tridiagonal and dense."""
+    rng = np.random.default_rng(1000 + N)
+    f = len(omegas)
+    X = rng.uniform(-10, 10, (41, f))
+    X[0] = 0.0
+    c = make_const(N, omegas)
+    scale = 1.0 + 0.02 * N * N                      # phases reach |e t| ~ N^2 * 10 * 25: eps-level errors scale with it
+    for site in (f - 1, 0):
+        _compare(native, O, c, X, site, loss_atol=2e-10 * scale, grad_rtol=5e-8 * scale)
+    prob = native.Problem.from_const(c)
+    tr = prob.trace(X, f - 1).cpu().numpy()
+    assert np.abs(tr - O.trace(c, X, f - 1)).max() < 3e-10 * scale * max(1, N)
+    prob.close()
+
+
+def test_register_and_shared_memory_large_d_paths_agree():
+    """QTET_BIG_SMEM=1 keeps the older shared-memory kernels of the large-d path: both families must agree."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = f"""
+import sys, numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'quantum-targeted-energy-transfer_b200')!r})
+from tet import _native
+out = []
+for N, om in [(10, [-3, 3, 3]), (60, [-3, 3])]:
+    c = {{"max_N": N, "sites": len(om), "max_t": 25, "omegas": om, "chis": [0] * len(om), "coupling": 1, "timesteps": 30}}
+    X = np.random.default_rng(5).uniform(-10, 10, (300, len(om)))
+    p = _native.Problem.from_const(c)
+    L, g, k = p.loss_grad_host(X, len(om) - 1)
+    out.append((L, g, k))
+np.savez(sys.argv[1], *[a for t in out for a in t])
+"""
+    import tempfile
+    res = []
+    for env in ({}, {"QTET_BIG_SMEM": "1"}):
+        with tempfile.NamedTemporaryFile(suffix=".npz") as fh:
+            out = subprocess.run([sys.executable, "-c", code, fh.name], env={**os.environ, **env}, capture_output=True, text=True, timeout=900)
+            assert out.returncode == 0, out.stderr[-2000:]
+            z = np.load(fh.name)
+            res.append([z[k] for k in z.files])
+    for a, b in zip(res[0], res[1]):
+        if a.dtype.kind == "i":
+            assert (a == b).mean() > 0.995
+        else:
+            assert np.abs(a - b).max() < 1e-6 * max(1.0, np.abs(b).max())
+
+
 def test_golden_reference_vectors(native, golden):
     # values produced by the reference's own HamiltonianLoss.py (c128 stand-in arithmetic)
     for r in golden["loss"]:
