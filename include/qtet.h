@@ -120,7 +120,8 @@ int qtet_argmin(const double* values_dev, int64_t B, double* min_dev, int64_t* i
 int qtet_fp64_peak(int device, double seconds_budget, double* tflops_out);
 
 /* Per-kernel timing (CUDA events on the launching streams).  kind 0: scalar QL kernel, 1: rotation-replay /
- * evolution / gradient kernel (the dominant one), 2: fused generic kernel.  enable(on=1) clears the records;
+ * evolution / gradient kernel (the dominant one), 2: fused generic kernel, or the
+ * Householder kernel of the dense large-d path.  enable(on=1) clears the records;
  * read() synchronises the device and returns, per kind, the summed duration [ms], the number of launches and
  * the number of parameter points they processed (arrays of 3). */
 int qtet_profile_enable(qtet_problem* p, int on);

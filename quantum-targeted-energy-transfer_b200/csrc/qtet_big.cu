@@ -56,12 +56,19 @@ struct BigQlArgs {
     int* overflow_count;
 };
 
+// Storage of the lane's tridiagonal: shared memory [2k + {0,1}][lane] (bank = lane), or -- LOCAL -- per-thread arrays
+// in local memory (L1/L2-cached, lane-interleaved by the hardware).  The shared layout caps the kernel at
+// 228 KB / (2 d 256 B) warps per SM (4 at d = 101), which leaves the serial rsqrt/FMA chain of a sweep exposed; the
+// local layout trades some L2 traffic for 4x the resident warps.
+template <bool LOCAL>
 struct QlLaneBig {
-    double* arr;       // diag k at arr[64 k], off k at arr[64 k + 32]
+    double* arr;       // shared: diag k at arr[64 k], off k at arr[64 k + 32]
+    double ld[LOCAL ? 128 : 1];
+    double lo[LOCAL ? 128 : 1];
     int d;
-    __device__ __forceinline__ double& dg(int k) const { return arr[64 * k]; }
-    __device__ __forceinline__ double& of(int k) const { return arr[64 * k + 32]; }
-    __device__ __forceinline__ Mask128 scan_small() const {
+    __device__ __forceinline__ double& dg(int k) { if constexpr (LOCAL) return ld[k]; else return arr[64 * k]; }
+    __device__ __forceinline__ double& of(int k) { if constexpr (LOCAL) return lo[k]; else return arr[64 * k + 32]; }
+    __device__ __forceinline__ Mask128 scan_small() {
         Mask128 m;
         m.set(d - 1);
         for (int k = 0; k < d - 1; ++k) {
@@ -70,7 +77,7 @@ struct QlLaneBig {
         }
         return m;
     }
-    __device__ __forceinline__ double wilkinson_g(int l, int m) const {
+    __device__ __forceinline__ double wilkinson_g(int l, int m) {
         const double dl = dg(l), el = of(l);
         const double gg = (dg(l + 1) - dl) / (2.0 * el);
         const double rr = sqrt(fma(gg, gg, 1.0));
@@ -78,13 +85,14 @@ struct QlLaneBig {
     }
 };
 
+template <bool LOCAL>
 __global__ void __launch_bounds__(kWarpsBig * 32) ql_scalar_big_kernel(BigQlArgs a) {
     extern __shared__ double sm[];
     const ProblemView& pv = a.pv;
     const int d = pv.d, f = pv.f;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    QlLaneBig t;
-    t.arr = sm + (size_t)warp * 2 * d * 32 + lane;
+    QlLaneBig<LOCAL> t;
+    t.arr = LOCAL ? nullptr : sm + (size_t)warp * 2 * d * 32 + lane;
     t.d = d;
     const long long nbatch = (a.n + 31) / 32;
     for (long long batch = (long long)blockIdx.x * kWarpsBig + warp; batch < nbatch; batch += (long long)gridDim.x * kWarpsBig) {
@@ -259,6 +267,8 @@ struct BigWorkspace {
     int* overflow_count = nullptr;
     unsigned short* pair_tab = nullptr;   // register-resident replay: index pairs of the padded dimension
     int regD = 0;                         // padded dimension of the register-resident kernels, 0 = shared-memory kernels
+    bool ql_local = false;                // scalar QL keeps the tridiagonal in local memory (more resident warps)
+    int ql_ctas = 8;                      // ... CTAs of kWarpsBig warps per SM in that mode
 };
 
 bool big_eligible(const ProblemView& pv) {
@@ -298,6 +308,8 @@ int launch_big(const ProblemView& pv, BigWorkspace** wsp, const double* chis, in
         QTET_CUDA(cudaMalloc(&ws->overflow_count, sizeof(int)));
         // rows in registers when the dimension fits (d <= 101); QTET_BIG_SMEM=1 keeps the shared-memory kernels (cross-check)
         ws->regD = (std::getenv("QTET_BIG_SMEM") || pv.T > bigreg_max_timesteps()) ? 0 : bigreg_padded_dim(d);
+        ws->ql_local = true; ws->ql_ctas = 16;
+        if (const char* env = std::getenv("QTET_QL_LOCAL")) { ws->ql_local = std::atoi(env) > 0; if (std::atoi(env) > 1) ws->ql_ctas = std::atoi(env); }
         if (ws->regD) {
             std::vector<unsigned short> tab;
             for (int i = 0; i < ws->regD; ++i)
@@ -310,7 +322,21 @@ int launch_big(const ProblemView& pv, BigWorkspace** wsp, const double* chis, in
     const bool dense = !pv.tridiag;
     const size_t per_batch = (size_t)ws->capit * 32 * sizeof(double2) + (size_t)ws->maxr * 32 * 4 + (size_t)ws->maxr * 4 + 4 +
                              32 * ((size_t)d * 8 + 4 + (dense ? (2 * (size_t)d * 8 + (size_t)d * d * 8) : 0));
-    long long chunk_b = (long long)((size_t)4 << 30) / (long long)per_batch;      // <= 4 GiB in flight
+    // The scalar QL kernel is a serial chain per point (milliseconds per batch of 32 points, whatever the machine
+    // load): its cost is amortised only if MANY batches are in flight, so the chunk takes what the card can spare --
+    // up to 40 % of the free HBM, at most 48 GiB (B200: 180 GB) -- rather than a fixed few GiB.
+    size_t budget = (size_t)4 << 30;
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const size_t avail = free_b + ws->blob_bytes;           // our own blob is reusable
+            size_t want = (size_t)(0.4 * (double)avail);
+            if (want > ((size_t)48 << 30)) want = (size_t)48 << 30;
+            if (want > budget) budget = want;
+        } else cudaGetLastError();
+        if (const char* env = std::getenv("QTET_BIG_WS_GIB")) { const double g = std::atof(env); if (g > 0) budget = (size_t)(g * 1073741824.0); }
+    }
+    long long chunk_b = (long long)budget / (long long)per_batch;
     if (chunk_b < 64) chunk_b = 64;
     const long long all_b = (B + 31) / 32;
     if (chunk_b > all_b) chunk_b = all_b;
@@ -339,12 +365,15 @@ int launch_big(const ProblemView& pv, BigWorkspace** wsp, const double* chis, in
     if (dense) { bs.tri_d = (double*)(ws->blob + o_trid); bs.tri_e = (double*)(ws->blob + o_trie); bs.qmat = (double*)(ws->blob + o_q); }
     int* overflow_list = (int*)(ws->blob + o_list);
 
-    const size_t smemA = (size_t)kWarpsBig * 2 * d * 32 * sizeof(double);
-    QTET_CUDA(cudaFuncSetAttribute(ql_scalar_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
-    QTET_CUDA(cudaFuncSetAttribute(ql_scalar_big_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    const bool ql_local = ws->ql_local;
+    const size_t smemA = ql_local ? 0 : (size_t)kWarpsBig * 2 * d * 32 * sizeof(double);
+    auto qlk = ql_local ? ql_scalar_big_kernel<true> : ql_scalar_big_kernel<false>;
+    QTET_CUDA(cudaFuncSetAttribute(qlk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+    QTET_CUDA(cudaFuncSetAttribute(qlk, cudaFuncAttributePreferredSharedMemoryCarveout, ql_local ? 0 : 100));
     int per_sm_a = 0;
-    QTET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, ql_scalar_big_kernel, kWarpsBig * 32, smemA));
+    QTET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, qlk, kWarpsBig * 32, smemA));
     if (per_sm_a < 1) per_sm_a = 1;
+    if (ql_local && per_sm_a > ws->ql_ctas) per_sm_a = ws->ql_ctas;
 
     for (long long lo = 0; lo < B; lo += chunk) {
         const long long n = (B - lo < chunk) ? (B - lo) : chunk;
@@ -369,7 +398,7 @@ int launch_big(const ProblemView& pv, BigWorkspace** wsp, const double* chis, in
         const long long needA = ((n + 31) / 32 + kWarpsBig - 1) / kWarpsBig;
         if (gridA > needA) gridA = needA;
         if (prof) prof->begin(0, n, st);
-        ql_scalar_big_kernel<<<(unsigned)gridA, kWarpsBig * 32, smemA, st>>>(qa);
+        qlk<<<(unsigned)gridA, kWarpsBig * 32, smemA, st>>>(qa);
         count_launch();
         if (prof) prof->finish(0, st);
         QTET_CUDA(cudaGetLastError());

@@ -159,10 +159,11 @@ class Problem:
         _check(lib.qtet_profile_enable(self._h, 1 if on else 0), "qtet_profile_enable")
 
     def profile_read(self):
-        """{kernel: (ms_sum, launches, points)} for 'ql_scalar', 'apply', 'generic'."""
+        """{kernel: (ms_sum, launches, points)} for 'ql_scalar' (thread-per-point QL), 'apply' (rotation replay + evolution + gradient),
+        'generic_or_householder' (fused generic kernel, or the Householder kernel of the dense large-d path)."""
         ms = (C.c_double * 3)(); n = (C.c_int64 * 3)(); pts = (C.c_int64 * 3)()
         _check(lib.qtet_profile_read(self._h, ms, n, pts), "qtet_profile_read")
-        return {k: (ms[i], int(n[i]), int(pts[i])) for i, k in enumerate(("ql_scalar", "apply", "generic"))}
+        return {k: (ms[i], int(n[i]), int(pts[i])) for i, k in enumerate(("ql_scalar", "apply", "generic_or_householder"))}
 
     # ---- the hot path --------------------------------------------------------------------
     def _site(self, site) -> int:
