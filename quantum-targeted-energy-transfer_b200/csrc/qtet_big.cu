@@ -365,15 +365,22 @@ int launch_big(const ProblemView& pv, BigWorkspace** wsp, const double* chis, in
     if (dense) { bs.tri_d = (double*)(ws->blob + o_trid); bs.tri_e = (double*)(ws->blob + o_trie); bs.qmat = (double*)(ws->blob + o_q); }
     int* overflow_list = (int*)(ws->blob + o_list);
 
-    const bool ql_local = ws->ql_local;
-    const size_t smemA = ql_local ? 0 : (size_t)kWarpsBig * 2 * d * 32 * sizeof(double);
+    // Scalar QL storage: the shared-memory variant has the shorter chain per batch but only 228 KB / (2 d 256 B) warps
+    // per SM; when a chunk holds more batches than that many slots the local-memory variant (4x the warps) wins.
+    const size_t smem_sh = (size_t)kWarpsBig * 2 * d * 32 * sizeof(double);
+    QTET_CUDA(cudaFuncSetAttribute(ql_scalar_big_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sh));
+    QTET_CUDA(cudaFuncSetAttribute(ql_scalar_big_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    int per_sm_sh = 0, per_sm_lo = 0;
+    QTET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_sh, ql_scalar_big_kernel<false>, kWarpsBig * 32, smem_sh));
+    QTET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_lo, ql_scalar_big_kernel<true>, kWarpsBig * 32, 0));
+    if (per_sm_sh < 1) per_sm_sh = 1;
+    if (per_sm_lo < 1) per_sm_lo = 1;
+    if (per_sm_lo > ws->ql_ctas) per_sm_lo = ws->ql_ctas;
+    const long long slots_sh = (long long)ws->sms * per_sm_sh * kWarpsBig;
+    const bool ql_local = ws->ql_local && chunk_b > slots_sh;
+    const size_t smemA = ql_local ? 0 : smem_sh;
     auto qlk = ql_local ? ql_scalar_big_kernel<true> : ql_scalar_big_kernel<false>;
-    QTET_CUDA(cudaFuncSetAttribute(qlk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
-    QTET_CUDA(cudaFuncSetAttribute(qlk, cudaFuncAttributePreferredSharedMemoryCarveout, ql_local ? 0 : 100));
-    int per_sm_a = 0;
-    QTET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, qlk, kWarpsBig * 32, smemA));
-    if (per_sm_a < 1) per_sm_a = 1;
-    if (ql_local && per_sm_a > ws->ql_ctas) per_sm_a = ws->ql_ctas;
+    const int per_sm_a = ql_local ? per_sm_lo : per_sm_sh;
 
     for (long long lo = 0; lo < B; lo += chunk) {
         const long long n = (B - lo < chunk) ? (B - lo) : chunk;
