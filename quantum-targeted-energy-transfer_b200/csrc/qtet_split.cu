@@ -307,7 +307,7 @@ struct BLayout {
     // shared memory per warp, in doubles
     static constexpr int RING = kRing * SLOT_ROWS * PPW * 2;           // double2 [kRing][SLOT_ROWS][PPW]
     static constexpr int HDR = kMaxRounds * PPW / 2;                   // unsigned [kMaxRounds][PPW]
-    static constexpr int ZB = 2 * PPW * D * 2;                         // double2 [2][PPW][D]
+    static constexpr int ZB = 4 * PPW * D * 2;                         // double2 [2 passes][2 samples][PPW][D]
     static constexpr int LV = 8 * PPW * D;                             // double [8][PPW][D]
     static constexpr int PART = PPW * G * DH * 2;                      // double2 [PPW][G][DH]
     static constexpr int SM_S = PPW * (D + NP);                        // double [PPW][D + NP]
@@ -467,42 +467,52 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) apply_kernel(SplitArgs a) {
         // ---- time evolution: n(t_k) = sum_rows n_site |psi_row(t_k)|^2, running arg-max / arg-min
         int kbest = 0;
         double vbest = 0.0;
-        for (int k = 0; k < T; ++k) {
-            double2* zb = zbuf + ((k & 1) * PPW + g) * D;
+        // two samples per pass: every V element is read once for four fmas (operand reuse), the pass overhead halves
+        for (int k = 0; k < T; k += 2) {
+            double2* zb0 = zbuf + ((((k >> 1) & 1) * 2 + 0) * PPW + g) * D;
+            double2* zb1 = zbuf + ((((k >> 1) & 1) * 2 + 1) * PPW + g) * D;
 #pragma unroll
             for (int t = 0; t < RZ; ++t) {
                 const int i = q + t * G;
-                if (i < D) zb[i] = make_double2(zr[t], zi[t]);
+                const double nr_ = fma(zr[t], wre[t], -(zi[t] * wim[t]));
+                const double ni_ = fma(zr[t], wim[t], zi[t] * wre[t]);
+                if (i < D) { zb0[i] = make_double2(zr[t], zi[t]); zb1[i] = make_double2(nr_, ni_); }
+                zr[t] = fma(nr_, wre[t], -(ni_ * wim[t]));
+                zi[t] = fma(nr_, wim[t], ni_ * wre[t]);
             }
             __syncwarp();
-            double pr[R][2], pi[R][2];
+            double pr0[R], pi0[R], pr1[R], pi1[R];
 #pragma unroll
-            for (int kk = 0; kk < R; ++kk) { pr[kk][0] = pr[kk][1] = 0.0; pi[kk][0] = pi[kk][1] = 0.0; }
+            for (int kk = 0; kk < R; ++kk) { pr0[kk] = pi0[kk] = pr1[kk] = pi1[kk] = 0.0; }
 #pragma unroll
             for (int i = 0; i < D; ++i) {
-                const double2 z = zb[i];
+                const double2 za = zb0[i], zc = zb1[i];
 #pragma unroll
                 for (int kk = 0; kk < R; ++kk) {
-                    pr[kk][i & 1] = fma(v[kk][i], z.x, pr[kk][i & 1]);
-                    pi[kk][i & 1] = fma(v[kk][i], z.y, pi[kk][i & 1]);
+                    pr0[kk] = fma(v[kk][i], za.x, pr0[kk]);
+                    pi0[kk] = fma(v[kk][i], za.y, pi0[kk]);
+                    pr1[kk] = fma(v[kk][i], zc.x, pr1[kk]);
+                    pi1[kk] = fma(v[kk][i], zc.y, pi1[kk]);
                 }
             }
-            double part_n = 0.0;
+            double part0 = 0.0, part1 = 0.0;
 #pragma unroll
             for (int kk = 0; kk < R; ++kk) {
-                const double re = pr[kk][0] + pr[kk][1], im = pi[kk][0] + pi[kk][1];
-                part_n = fma(wsite[kk], fma(re, re, im * im), part_n);
+                part0 = fma(wsite[kk], fma(pr0[kk], pr0[kk], pi0[kk] * pi0[kk]), part0);
+                part1 = fma(wsite[kk], fma(pr1[kk], pr1[kk], pi1[kk] * pi1[kk]), part1);
             }
-            const double nk = group_sum<G>(part_n);
-            if (a.trace && valid && q == (k % G)) a.trace[p * T + k] = nk;
-            const double key = a.acceptor ? nk : -nk;
-            if (k == 0 || key > vbest) { vbest = key; kbest = k; }          // first extremum wins ties
 #pragma unroll
-            for (int t = 0; t < RZ; ++t) {
-                const double nr_ = fma(zr[t], wre[t], -(zi[t] * wim[t]));
-                zi[t] = fma(zr[t], wim[t], zi[t] * wre[t]);
-                zr[t] = nr_;
+            for (int o = G / 2; o > 0; o >>= 1) {
+                part0 += __shfl_xor_sync(0xffffffffu, part0, o);
+                part1 += __shfl_xor_sync(0xffffffffu, part1, o);
             }
+            if (a.trace && valid) {
+                if (q == (k % G)) a.trace[p * T + k] = part0;
+                if (k + 1 < T && q == ((k + 1) % G)) a.trace[p * T + k + 1] = part1;
+            }
+            const double key0 = a.acceptor ? part0 : -part0, key1 = a.acceptor ? part1 : -part1;
+            if (k == 0 || key0 > vbest) { vbest = key0; kbest = k; }        // first extremum wins ties
+            if (k + 1 < T && key1 > vbest) { vbest = key1; kbest = k + 1; }
         }
         if (q == 0 && valid) {
             if (a.loss) a.loss[p] = a.acceptor ? ((double)pv.N - vbest) : -vbest;

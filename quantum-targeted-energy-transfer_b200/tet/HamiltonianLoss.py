@@ -51,3 +51,28 @@ class Loss:
     def createHamiltonian(self):
         """HamiltonianLoss.py:168-176 for the current self.chis (device-built, returned as numpy)."""
         return self.problem.hamiltonian([_as_float(c) for c in self.chis])
+
+    # ---- the reference's remaining public methods, kept so that code poking at a Loss object still runs ----------
+    def derive(self):
+        """HamiltonianLoss.py:62-110: (re)fill self.states with the Fock basis in the reference's order."""
+        self.states = self.problem.states()
+
+    def getHash(self, state):
+        """HamiltonianLoss.py:112-116."""
+        s = 0
+        for i in range(self.sites):
+            s += np.sqrt(100 * (i + 1) + 3) * state[i]
+        return s
+
+    def getHashArray(self):
+        """HamiltonianLoss.py:118-121."""
+        self.T = np.array([self.getHash(self.states[i]) for i in range(self.dim)])
+        self.sorted_indices = np.argsort(self.T)
+
+    def ConstructElement(self, n, m):
+        """HamiltonianLoss.py:124-165: H[n, m] for the current self.chis."""
+        return self.createHamiltonian()[n, m]
+
+    def loss(self, single_value=True):
+        """HamiltonianLoss.py:218-233 for the current self.chis / self.targetState."""
+        return self(self.chis, self.targetState, single_value)

@@ -118,6 +118,13 @@ def test_tet_api_loss_and_optimizer(native, O, tmp_path):
     assert tr.shape == (30,) and np.abs(tr - O.trace(c, [1.5, -1.5], 0)).max() < 1e-10
     with pytest.raises(ValueError):
         L([1.5, -1.5], site=1.5)
+    # the reference's remaining public methods (HamiltonianLoss.py:62-176, 218-233)
+    L([1.5, -1.5], site=1)
+    assert abs(float(L.loss().numpy()) - O.loss(c, [1.5, -1.5], 1)) < 1e-10
+    H = O.hamiltonian(c, [1.5, -1.5])
+    assert L.ConstructElement(2, 2) == H[2, 2] and L.ConstructElement(2, 3) == H[2, 3]
+    L.derive(); L.getHashArray()
+    assert (L.states == O.fock_basis(4, 2)).all() and L.sorted_indices[0] == 0
     opt = tet.Optimizer(const=c, target_site=1, Print=False, iterations=500, train_sites=[0, 1],
                         opt=Adam(learning_rate=0.1, beta_1=0.9, amsgrad=False), data_path=str(tmp_path / "g0"))
     res = opt(0.5, -0.5, write_data=True)
