@@ -46,11 +46,11 @@ int ensure_scratch(qtet_problem* p, size_t bytes) {
 }
 
 int loss_grad_dispatch(qtet_problem* p, const double* chis, int64_t B, int site, double* loss,
-                       double* grad, int32_t* tstar, double* trace, cudaStream_t st) {
+                       double* grad, int32_t* tstar, double* trace, cudaStream_t st, const ChunkHook* hook) {
     if (p->path == QTET_PATH_SPLIT && !split_eligible(p->view))
         return launch_big(p->view, &p->big_ws, chis, B, site, loss, grad, tstar, trace, st, p->prof.on ? &p->prof : nullptr);
     if (p->path == QTET_PATH_SPLIT)
-        return launch_split(p->view, &p->split_ws, chis, B, site, loss, grad, tstar, trace, st, p->prof.on ? &p->prof : nullptr);
+        return launch_split(p->view, &p->split_ws, chis, B, site, loss, grad, tstar, trace, st, p->prof.on ? &p->prof : nullptr, hook);
     return launch_generic(p->view, chis, B, site, loss, grad, tstar, trace, st, p->prof.on ? &p->prof : nullptr);
 }
 
@@ -162,6 +162,13 @@ void qtet_problem_destroy(qtet_problem* p) {
     cudaSetDevice(p->device);
     if (p->dev_blob) cudaFree(p->dev_blob);
     if (p->scratch) cudaFree(p->scratch);
+    if (p->s_in) cudaStreamDestroy(p->s_in);
+    if (p->s_run) cudaStreamDestroy(p->s_run);
+    if (p->s_out) cudaStreamDestroy(p->s_out);
+    for (int i = 0; i < qtet_problem::kMaxSlices; ++i) {
+        if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);
+        if (p->ev_run[i]) cudaEventDestroy(p->ev_run[i]);
+    }
     split_workspace_free(p->split_ws);
     big_workspace_free(p->big_ws);
     p->prof.clear();
@@ -240,14 +247,59 @@ int qtet_loss_grad_host(qtet_problem* p, const double* chis_host, int64_t B, int
     double* dloss = (double*)(base + nb_chi);
     double* dgrad = (double*)(base + nb_chi + nb_loss);
     int32_t* dts = (int32_t*)(base + nb_chi + nb_loss + nb_grad);
-    cudaStream_t st = nullptr;
-    QTET_CUDA(cudaMemcpyAsync(dchi, chis_host, nb_chi, cudaMemcpyHostToDevice, st));
-    rc = loss_grad_dispatch(p, dchi, B, target_site, dloss, grad_host ? dgrad : nullptr, tstar_host ? dts : nullptr, nullptr, st);
-    if (rc) return rc;
-    QTET_CUDA(cudaMemcpyAsync(loss_host, dloss, nb_loss, cudaMemcpyDeviceToHost, st));
-    if (grad_host) QTET_CUDA(cudaMemcpyAsync(grad_host, dgrad, nb_grad, cudaMemcpyDeviceToHost, st));
-    if (tstar_host) QTET_CUDA(cudaMemcpyAsync(tstar_host, dts, nb_t, cudaMemcpyDeviceToHost, st));
-    QTET_CUDA(cudaStreamSynchronize(st));
+    // H2D, kernels and D2H run on three streams.  The register split path processes the batch in chunks (two workspace
+    // buffers, qtet_split.cu); the copies hang on its per-chunk hooks, so the inputs of chunk c+1 arrive and the results of
+    // chunk c-1 leave while chunk c computes.  The other paths copy the whole batch before / after their single launch
+    // sequence (the large-d path wants every batch it can get in one launch: scalar QL latency, qtet_big.cu).
+    if (!p->s_in) {
+        QTET_CUDA(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
+        QTET_CUDA(cudaStreamCreateWithFlags(&p->s_run, cudaStreamNonBlocking));
+        QTET_CUDA(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < qtet_problem::kMaxSlices; ++i) {
+            QTET_CUDA(cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
+            QTET_CUDA(cudaEventCreateWithFlags(&p->ev_run[i], cudaEventDisableTiming));
+        }
+    }
+    struct Ctx {
+        qtet_problem* p; size_t f;
+        const double* chis_host; double* dchi;
+        double* loss_host; double* dloss; double* grad_host; double* dgrad; int32_t* tstar_host; int32_t* dts;
+        int nin, nout;
+    } cx{p, f, chis_host, dchi, loss_host, dloss, grad_host, dgrad, tstar_host, dts, 0, 0};
+    auto copy_in = [](void* c_, long long lo, long long n, cudaStream_t consumer) -> int {
+        Ctx& c = *(Ctx*)c_;
+        cudaEvent_t ev = c.p->ev_in[c.nin++ % qtet_problem::kMaxSlices];
+        QTET_CUDA(cudaMemcpyAsync(c.dchi + lo * c.f, c.chis_host + lo * c.f, (size_t)n * c.f * 8, cudaMemcpyHostToDevice, c.p->s_in));
+        QTET_CUDA(cudaEventRecord(ev, c.p->s_in));
+        QTET_CUDA(cudaStreamWaitEvent(consumer, ev, 0));
+        return QTET_OK;
+    };
+    auto copy_out = [](void* c_, long long lo, long long n, cudaStream_t producer) -> int {
+        Ctx& c = *(Ctx*)c_;
+        cudaEvent_t ev = c.p->ev_run[c.nout++ % qtet_problem::kMaxSlices];
+        QTET_CUDA(cudaEventRecord(ev, producer));
+        QTET_CUDA(cudaStreamWaitEvent(c.p->s_out, ev, 0));
+        QTET_CUDA(cudaMemcpyAsync(c.loss_host + lo, c.dloss + lo, (size_t)n * 8, cudaMemcpyDeviceToHost, c.p->s_out));
+        if (c.grad_host) QTET_CUDA(cudaMemcpyAsync(c.grad_host + lo * c.f, c.dgrad + lo * c.f, (size_t)n * c.f * 8, cudaMemcpyDeviceToHost, c.p->s_out));
+        if (c.tstar_host) QTET_CUDA(cudaMemcpyAsync(c.tstar_host + lo, c.dts + lo, (size_t)n * 4, cudaMemcpyDeviceToHost, c.p->s_out));
+        return QTET_OK;
+    };
+    const bool chunked = (p->path == QTET_PATH_SPLIT && split_eligible(p->view));
+    if (chunked) {
+        ChunkHook hook;
+        hook.ctx = &cx; hook.before = copy_in; hook.after = copy_out;
+        rc = loss_grad_dispatch(p, dchi, B, target_site, dloss, grad_host ? dgrad : nullptr, tstar_host ? dts : nullptr, nullptr, p->s_run, &hook);
+        if (rc) return rc;
+    } else {
+        rc = copy_in(&cx, 0, B, p->s_run);
+        if (rc) return rc;
+        rc = loss_grad_dispatch(p, dchi, B, target_site, dloss, grad_host ? dgrad : nullptr, tstar_host ? dts : nullptr, nullptr, p->s_run);
+        if (rc) return rc;
+        rc = copy_out(&cx, 0, B, p->s_run);
+        if (rc) return rc;
+    }
+    QTET_CUDA(cudaStreamSynchronize(p->s_out));
+    QTET_CUDA(cudaStreamSynchronize(p->s_run));
     return QTET_OK;
 }
 

@@ -68,10 +68,20 @@ struct Profiler {
     }
 };
 
+// Optional per-chunk hooks of the split path (the host-buffer entry point hangs its H2D / D2H copies on them):
+// `before` runs when chunk [lo, lo+n) is about to be queued (its inputs are first read on `aux`), `after` once everything
+// that writes the chunk's outputs has been queued on `st`.
+struct ChunkHook {
+    void* ctx = nullptr;
+    int (*before)(void* ctx, long long lo, long long n, cudaStream_t aux) = nullptr;
+    int (*after)(void* ctx, long long lo, long long n, cudaStream_t st) = nullptr;
+};
+
 struct SplitWorkspace;   // rotation streams etc. (qtet_split.cu)
 bool split_eligible(const ProblemView& pv);
 int launch_split(const ProblemView& pv, SplitWorkspace** ws, const double* chis, int64_t B, int site,
-                 double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st, Profiler* prof = nullptr);
+                 double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st, Profiler* prof = nullptr,
+                 const ChunkHook* hook = nullptr);
 void split_workspace_free(SplitWorkspace* ws);
 
 struct BigWorkspace;     // large-d split path (qtet_big.cu)
@@ -100,12 +110,16 @@ struct qtet_problem {
     // scratch for *_host convenience calls and the optimiser
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    // copy/compute pipeline of qtet_loss_grad_host: H2D, kernels and D2H of consecutive slices overlap
+    static constexpr int kMaxSlices = 64;
+    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[kMaxSlices] = {}, ev_run[kMaxSlices] = {};
 };
 
 namespace qtet {
 int ensure_scratch(qtet_problem* p, size_t bytes);
 int loss_grad_dispatch(qtet_problem* p, const double* chis, int64_t B, int site, double* loss,
-                       double* grad, int32_t* tstar, double* trace, cudaStream_t st);
+                       double* grad, int32_t* tstar, double* trace, cudaStream_t st, const ChunkHook* hook = nullptr);
 }
 
 // ---- device helpers ---------------------------------------------------------------------

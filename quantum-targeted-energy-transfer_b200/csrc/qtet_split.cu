@@ -765,7 +765,8 @@ int launch_generic_list(const ProblemView& pv, const double* chis, const int* li
                         int site, double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st);
 
 int launch_split(const ProblemView& pv, SplitWorkspace** wsp, const double* chis, int64_t B, int site,
-                 double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st, Profiler* prof) {
+                 double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st, Profiler* prof,
+                 const ChunkHook* hook) {
     if (B <= 0) return QTET_OK;
     if (!split_eligible(pv)) { set_error("split path not eligible for this problem"); return QTET_EUNSUPPORTED; }
     SplitWorkspace* ws = *wsp;
@@ -851,6 +852,7 @@ int launch_split(const ProblemView& pv, SplitWorkspace** wsp, const double* chis
         a.trace = trace ? trace + lo * pv.T : nullptr;
         // K_A(c) on aux, after K_B(c-2) released this buffer
         if (c >= 2) QTET_CUDA(cudaStreamWaitEvent(ws->aux, ws->ev_b[buf], 0));
+        if (hook && hook->before) { const int hrc = hook->before(hook->ctx, lo, n, ws->aux); if (hrc) return hrc; }
         QTET_CUDA(cudaMemsetAsync(a.overflow_count, 0, sizeof(int), ws->aux));
         long long gridA = (long long)ws->sms * per_sm_a;
         const long long needA = ((n + 31) / 32 + kWarpsA - 1) / kWarpsA;
@@ -879,6 +881,7 @@ int launch_split(const ProblemView& pv, SplitWorkspace** wsp, const double* chis
         rc = launch_generic_list(pv, a.chis, a.overflow_list, a.overflow_count, n, site, a.loss, a.grad, a.tstar, a.trace, st);
         if (rc) return rc;
         QTET_CUDA(cudaEventRecord(ws->ev_b[buf], st));
+        if (hook && hook->after) { const int hrc = hook->after(hook->ctx, lo, n, st); if (hrc) return hrc; }
     }
     return QTET_OK;
 }
