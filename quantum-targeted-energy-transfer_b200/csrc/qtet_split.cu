@@ -67,6 +67,16 @@ __device__ __forceinline__ unsigned lowmask(int l) { return (l >= 32) ? 0xffffff
 // it0 + (mtop-1-i) holds, for every lane, the rotation of plane i or the identity if the lane does not
 // touch that plane in this round.  Rows are written by all 32 lanes: fully coalesced 512 B stores.
 // ------------------------------------------------------------------------------------------------
+// 1/sqrt(x) for normal positive x: the hardware seed and one third-order step, i.e. what rsqrt() does on its fast path,
+// without the range check / slow-path branch (the callers guard x themselves).
+__device__ __forceinline__ double rsqrt_fast(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y * y, 1.0);
+    return fma(y * e, fma(e, 0.375, 0.5), y);
+}
+constexpr double kTinyR2 = 1e-280;        // below this a rotation is treated as underflowed (as r2 == 0)
+
 struct QlLane {
     double* arr;       // diag k at arr[64 k], off k at arr[64 k + 32]
     int d;
@@ -140,29 +150,33 @@ __global__ void __launch_bounds__(kWarpsA * 32) ql_scalar_kernel(SplitArgs a) {
                 double g = t.wilkinson_g(l, m);
                 double s = 1.0, c = 1.0, pp = 0.0, dnext = 0.0;
                 bool broke = false;
-                for (int i = m - 1; i >= l; --i) {
-                    const double ei = t.of(i);
-                    const double fo = s * ei, bo = c * ei;
+                // dg(i+1), dg(i), of(i) of the coming plane travel in registers: each diagonal entry is loaded once (it
+                // is read by two consecutive planes) and one plane ahead of its use, off the dependency chain
+                double* q = t.arr + 64 * (m - 1);             // &dg(i)
+                double d_hi = q[64], d_i = q[0], e_i = q[32];
+                unsigned fbit = 1u << m;
+                for (int i = m - 1; i >= l; --i, q -= 64) {
+                    const double* qn = (i > l) ? q - 64 : q;
+                    const double d_n = qn[0], e_n = qn[32];
+                    const double fo = s * e_i, bo = c * e_i;
                     const double r2 = fma(fo, fo, g * g);
-                    if (r2 == 0.0) { t.of(i + 1) = 0.0; t.dg(i + 1) -= pp; t.of(m) = 0.0; broke = true; break; }
-                    const double rinv = rsqrt(r2);
+                    if (r2 < kTinyR2) { q[96] = 0.0; q[64] = d_hi - pp; t.of(m) = 0.0; broke = true; break; }
+                    const double rinv = rsqrt_fast(r2);
                     const double r = r2 * rinv;
                     s = fo * rinv; c = g * rinv;
-                    g = t.dg(i + 1) - pp;
-                    const double rr = fma(t.dg(i) - g, s, 2.0 * c * bo);
+                    g = d_hi - pp;
+                    const double rr = fma(d_i - g, s, 2.0 * c * bo);
                     pp = s * rr;
                     const double dnew = g + pp;
-                    t.dg(i + 1) = dnew;
+                    q[64] = dnew;                              // dg(i+1)
                     g = fma(c, rr, -bo);
-                    if (i + 1 < m) {
-                        t.of(i + 1) = r;
-                        const unsigned bit = 1u << (i + 1);
-                        if (r <= kEps * (fabs(dnew) + fabs(dnext))) small |= bit; else small &= ~bit;
-                    }
-                    dnext = dnew;
+                    q[96] = r;                                 // of(i+1) (of(m) is reset below)
+                    small = (r <= kEps * (fabs(dnew) + fabs(dnext))) ? (small | fbit) : (small & ~fbit);
+                    fbit >>= 1;
+                    dnext = dnew; d_hi = d_i; d_i = d_n; e_i = e_n;
                 }
                 if (broke) { small = t.scan_small(); continue; }
-                const double dlnew = t.dg(l) - pp;
+                const double dlnew = d_hi - pp;                // d_hi = dg(l) after the last plane
                 t.dg(l) = dlnew; t.of(l) = g; t.of(m) = 0.0;
                 small |= 1u << m;
                 const unsigned bit = 1u << l;
@@ -201,32 +215,37 @@ __global__ void __launch_bounds__(kWarpsA * 32) ql_scalar_kernel(SplitArgs a) {
             }
             bool broke = false;
             double2* row = rec + (size_t)it * 32;
+            // as in pass 1: the coming plane's dg(i+1), dg(i), of(i) are carried in registers and loaded a plane ahead
+            double* q = t.arr + 64 * (done ? 0 : (m - 1));
+            double d_hi = 0.0, d_i = 0.0, e_i = 0.0;
+            if (!done) { d_hi = q[64]; d_i = q[0]; e_i = q[32]; }
+            unsigned fbit = done ? 0u : (1u << m);
             for (int i = mtop - 1; i >= lbot; --i, row += 32) {
                 double2 out = make_double2(1.0, 0.0);
                 if (!done && !broke && i < m && i >= l) {
-                    const double ei = t.of(i);
-                    const double fo = s * ei, bo = c * ei;
+                    const double* qn = (i > l) ? q - 64 : q;
+                    const double d_n = qn[0], e_n = qn[32];
+                    const double fo = s * e_i, bo = c * e_i;
                     const double r2 = fma(fo, fo, g * g);
-                    if (r2 == 0.0) {                       // underflow recovery: the rest of the sweep is identity
-                        t.of(i + 1) = 0.0; t.dg(i + 1) -= pp; t.of(m) = 0.0;
+                    if (r2 < kTinyR2) {                    // underflow recovery: the rest of the sweep is identity
+                        q[96] = 0.0; q[64] = d_hi - pp; t.of(m) = 0.0;
                         broke = true;
                     } else {
-                        const double rinv = rsqrt(r2);
+                        const double rinv = rsqrt_fast(r2);
                         const double r = r2 * rinv;
                         s = fo * rinv; c = g * rinv;
-                        g = t.dg(i + 1) - pp;
-                        const double rr = fma(t.dg(i) - g, s, 2.0 * c * bo);
+                        g = d_hi - pp;
+                        const double rr = fma(d_i - g, s, 2.0 * c * bo);
                         pp = s * rr;
                         const double dnew = g + pp;
-                        t.dg(i + 1) = dnew;
+                        q[64] = dnew;                      // dg(i+1)
                         g = fma(c, rr, -bo);
-                        if (i + 1 < m) {                   // off[i+1] = r is final: refresh its flag
-                            t.of(i + 1) = r;
-                            const unsigned bit = 1u << (i + 1);
-                            if (r <= kEps * (fabs(dnew) + fabs(dnext))) small |= bit; else small &= ~bit;
-                        }
-                        dnext = dnew;
+                        q[96] = r;                         // of(i+1) is final (of(m) is reset below): refresh its flag
+                        small = (r <= kEps * (fabs(dnew) + fabs(dnext))) ? (small | fbit) : (small & ~fbit);
+                        fbit >>= 1;
+                        dnext = dnew; d_hi = d_i; d_i = d_n; e_i = e_n;
                         out = make_double2(c, s);
+                        q -= 64;
                     }
                 }
                 *row = out;                                // all 32 lanes: one coalesced 512 B row
@@ -237,7 +256,7 @@ __global__ void __launch_bounds__(kWarpsA * 32) ql_scalar_kernel(SplitArgs a) {
             if (!done) {
                 if (broke) small = t.scan_small();         // rare path: rebuild the flags from scratch
                 else {
-                    const double dlnew = t.dg(l) - pp;
+                    const double dlnew = d_hi - pp;            // d_hi = dg(l) after the last plane
                     t.dg(l) = dlnew; t.of(l) = g; t.of(m) = 0.0;
                     small |= 1u << m;
                     const unsigned bit = 1u << l;
