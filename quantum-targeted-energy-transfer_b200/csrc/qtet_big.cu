@@ -46,6 +46,26 @@ struct Mask128 {
     }
 };
 
+// 1/sqrt(x) for normal positive x: hardware seed + one third-order step (rsqrt()'s fast path without its range check)
+__device__ __forceinline__ double rsqrt_fast(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y * y, 1.0);
+    return fma(y * e, fma(e, 0.375, 0.5), y);
+}
+constexpr double kTinyR2 = 1e-280;        // below this a rotation is treated as underflowed (as r2 == 0)
+
+// A single bit walking down a Mask128 (the flag of the off-diagonal a sweep has just finalised)
+struct WalkBit {
+    unsigned long long lo = 0ull, hi = 0ull;
+    __device__ __forceinline__ void at(int k) { lo = (k < 64) ? (1ull << k) : 0ull; hi = (k >= 64) ? (1ull << (k - 64)) : 0ull; }
+    __device__ __forceinline__ void down() { lo = (lo >> 1) | (hi << 63); hi >>= 1; }
+};
+__device__ __forceinline__ void put_bit(Mask128& m, const WalkBit& b, bool v) {
+    m.lo = v ? (m.lo | b.lo) : (m.lo & ~b.lo);
+    m.hi = v ? (m.hi | b.hi) : (m.hi & ~b.hi);
+}
+
 struct BigQlArgs {
     ProblemView pv;
     const double* chis;       // [n, f]
@@ -142,28 +162,32 @@ __global__ void __launch_bounds__(kWarpsBig * 32) ql_scalar_big_kernel(BigQlArgs
                 double g = t.wilkinson_g(l, m);
                 double s = 1.0, c = 1.0, pp = 0.0, dnext = 0.0;
                 bool broke = false;
+                // dg(i+1), dg(i), of(i) of the coming plane are carried in registers: every diagonal entry is loaded once
+                // (two consecutive planes read it) and one plane ahead of its use, off the dependency chain
+                double d_hi = t.dg(m), d_i = t.dg(m - 1), e_i = t.of(m - 1);
+                WalkBit fb; fb.at(m);
                 for (int i = m - 1; i >= l; --i) {
-                    const double ei = t.of(i);
-                    const double fo = s * ei, bo = c * ei;
+                    const int in = (i > l) ? i - 1 : i;
+                    const double d_n = t.dg(in), e_n = t.of(in);
+                    const double fo = s * e_i, bo = c * e_i;
                     const double r2 = fma(fo, fo, g * g);
-                    if (r2 == 0.0) { t.of(i + 1) = 0.0; t.dg(i + 1) -= pp; t.of(m) = 0.0; broke = true; break; }
-                    const double rinv = rsqrt(r2);
+                    if (r2 < kTinyR2) { t.of(i + 1) = 0.0; t.dg(i + 1) = d_hi - pp; t.of(m) = 0.0; broke = true; break; }
+                    const double rinv = rsqrt_fast(r2);
                     const double r = r2 * rinv;
                     s = fo * rinv; c = g * rinv;
-                    g = t.dg(i + 1) - pp;
-                    const double rr = fma(t.dg(i) - g, s, 2.0 * c * bo);
+                    g = d_hi - pp;
+                    const double rr = fma(d_i - g, s, 2.0 * c * bo);
                     pp = s * rr;
                     const double dnew = g + pp;
                     t.dg(i + 1) = dnew;
                     g = fma(c, rr, -bo);
-                    if (i + 1 < m) {
-                        t.of(i + 1) = r;
-                        small.put(i + 1, r <= kEps * (fabs(dnew) + fabs(dnext)));
-                    }
-                    dnext = dnew;
+                    t.of(i + 1) = r;                           // of(m) is reset below
+                    put_bit(small, fb, r <= kEps * (fabs(dnew) + fabs(dnext)));
+                    fb.down();
+                    dnext = dnew; d_hi = d_i; d_i = d_n; e_i = e_n;
                 }
                 if (broke) { small = t.scan_small(); continue; }
-                const double dlnew = t.dg(l) - pp;
+                const double dlnew = d_hi - pp;                // d_hi = dg(l) after the last plane
                 t.dg(l) = dlnew; t.of(l) = g; t.of(m) = 0.0;
                 small.set(m);
                 small.put(l, fabs(g) <= kEps * (fabs(dlnew) + fabs(dnext)));
@@ -205,30 +229,33 @@ __global__ void __launch_bounds__(kWarpsBig * 32) ql_scalar_big_kernel(BigQlArgs
             bool broke = false;
             // stream row it + (mtop-1-i) holds, for every lane, the rotation of plane i (identity if untouched)
             double2* row = rec + (size_t)it * 32;
+            double d_hi = 0.0, d_i = 0.0, e_i = 0.0;
+            WalkBit fb;
+            if (!done) { d_hi = t.dg(m); d_i = t.dg(m - 1); e_i = t.of(m - 1); fb.at(m); }
             for (int i = mtop - 1; i >= lbot; --i, row += 32) {
                 double2 out = make_double2(1.0, 0.0);
                 if (!done && !broke && i < m && i >= l) {
-                    const double ei = t.of(i);
-                    const double fo = s * ei, bo = c * ei;
+                    const int in = (i > l) ? i - 1 : i;
+                    const double d_n = t.dg(in), e_n = t.of(in);
+                    const double fo = s * e_i, bo = c * e_i;
                     const double r2 = fma(fo, fo, g * g);
-                    if (r2 == 0.0) {
-                        t.of(i + 1) = 0.0; t.dg(i + 1) -= pp; t.of(m) = 0.0;
+                    if (r2 < kTinyR2) {
+                        t.of(i + 1) = 0.0; t.dg(i + 1) = d_hi - pp; t.of(m) = 0.0;
                         broke = true;
                     } else {
-                        const double rinv = rsqrt(r2);
+                        const double rinv = rsqrt_fast(r2);
                         const double r = r2 * rinv;
                         s = fo * rinv; c = g * rinv;
-                        g = t.dg(i + 1) - pp;
-                        const double rr = fma(t.dg(i) - g, s, 2.0 * c * bo);
+                        g = d_hi - pp;
+                        const double rr = fma(d_i - g, s, 2.0 * c * bo);
                         pp = s * rr;
                         const double dnew = g + pp;
                         t.dg(i + 1) = dnew;
                         g = fma(c, rr, -bo);
-                        if (i + 1 < m) {
-                            t.of(i + 1) = r;
-                            small.put(i + 1, r <= kEps * (fabs(dnew) + fabs(dnext)));
-                        }
-                        dnext = dnew;
+                        t.of(i + 1) = r;                       // of(m) is reset below
+                        put_bit(small, fb, r <= kEps * (fabs(dnew) + fabs(dnext)));
+                        fb.down();
+                        dnext = dnew; d_hi = d_i; d_i = d_n; e_i = e_n;
                         out = make_double2(c, s);
                     }
                 }
@@ -238,7 +265,7 @@ __global__ void __launch_bounds__(kWarpsBig * 32) ql_scalar_big_kernel(BigQlArgs
             if (!done) {
                 if (broke) small = t.scan_small();
                 else {
-                    const double dlnew = t.dg(l) - pp;
+                    const double dlnew = d_hi - pp;            // d_hi = dg(l) after the last plane
                     t.dg(l) = dlnew; t.of(l) = g; t.of(m) = 0.0;
                     small.set(m);
                     small.put(l, fabs(g) <= kEps * (fabs(dlnew) + fabs(dnext)));
