@@ -30,6 +30,7 @@ combos = randomCombinations(lims, [0, 1], G, seed=0)
 lo, hi = parallel.shard_bounds(G, rank, ws)
 prob = _native.Problem.from_const(const)
 prob.adam_run(combos[lo:lo + 64], iterations=3)                      # warm-up (workspace allocation)
+parallel.global_argmin(np.zeros((1, 3)), lo, 2)                      # warm-up (NCCL communicator set-up)
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 out = prob.adam_run(combos[lo:hi], train_sites=(0, 1), iterations=1000, lr=0.1)
