@@ -371,8 +371,16 @@ struct RpLayout {
     static constexpr int R23 = R2 > R3 ? R2 : R3;
 };
 
+// Register budget for MINB CTAs of NW warps per SM.  (`__launch_bounds__(threads, MINB)` rounds a 3-warp CTA up to four
+// warps when it derives the cap -- 168 instead of 224 registers for three CTAs of 96 threads -- so the cap is given explicitly.)
+constexpr int reg_cap(int nw, int minb) {
+    int r = 65536 / (minb * nw * 32);
+    r = r / 8 * 8;
+    return r > 255 ? 255 : r;
+}
+
 template <int D, int NW, int MINB, int GS>
-__global__ void __launch_bounds__(NW * 32, MINB) replay_reg_kernel(RegArgs a) {
+__global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) replay_reg_kernel(RegArgs a) {
     using L = RpLayout<D, NW>;
     constexpr int NT = L::NT, DP = L::DP, LDV = L::LDV, NP = L::NP;
     constexpr int NG = (D - 1 + 2 * (kFuse - 1) + GS - 1) / GS;     // plane groups of GS steps per trip
@@ -833,7 +841,7 @@ int launch_replay_reg(const ProblemView& pv, const double* chis, int64_t n, int 
         case 16: return launch_replay_t<16, 1, 8, 4>(a, sms, st);
         case 32: return launch_replay_t<32, 1, 8, 4>(a, sms, st);
         case 48: return launch_replay_t<48, 2, 4, 4>(a, sms, st);
-        case 66: return launch_replay_t<66, 3, 3, 4>(a, sms, st);
+        case 66: return launch_replay_t<66, 3, 4, 4>(a, sms, st);
         case 84: return launch_replay_t<84, 3, 2, 4>(a, sms, st);
         case 101: return launch_replay_t<101, 4, 2, 2>(a, sms, st);
         default: break;
