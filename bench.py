@@ -60,14 +60,30 @@ def algorithmic_flops(d, T, tridiagonal):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock, power and throttle reasons sampled DURING the timed region: NVML from a thread every ~5 ms (pynvml),
+    `nvidia-smi -lms` as the fallback when the binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self._stop = index, [], None, None, False
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: map through CUDA_VISIBLE_DEVICES when it holds plain indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                idx = int(vis.split(",")[self.index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -77,20 +93,49 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        mx = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
+        bits = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+                "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+                "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4))}
+        reasons_fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                r = int(reasons_fn(self.handle))
+                row = [str(sm), str(mx), str(pw)] + [("Active" if (r & bits[k]) else "Not Active") for k in
+                                                     ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")]
+                self.rows.append((time.perf_counter(), row))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+    def stop(self, t_begin=None, t_end=None):
+        """Samples inside [t_begin, t_end] (the timed region).  If the region is shorter than the sampling period the samples
+        taken during the warm-up steps just before it (same load) are used, and counted separately."""
+        self._stop = True
+        if self.nvml is None and not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml / nvidia-smi unavailable"]}
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        else:
+            self.thread.join(timeout=1)
+        rows_all = list(self.rows)
+        inside = [r for t, r in rows_all if t_begin is None or (t_begin <= t <= (t_end if t_end is not None else t))]
+        rows = inside if inside else [r for t, r in rows_all if t_begin is None or t >= t_begin - 2.0]
         sm, mx, reasons, pw = [], [], set(), []
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
                 for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
@@ -99,7 +144,8 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "samples_in_timed_region": len(inside),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi", "reasons": sorted(reasons)}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -254,24 +300,32 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)            # started early: nvidia-smi takes a moment to deliver its first sample
+    sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
+    # keep the GPU under the same load until the sampler is live (untimed), so that short timed regions still get clocks
+    t_wait = time.perf_counter()
+    while not sampler.rows and time.perf_counter() - t_wait < 3.0:
+        step()
+        torch.cuda.synchronize()
+    barrier()
 
     prob.profile(True)                       # CUDA events around every kernel the library launches
-    sampler = ClockSampler(local)
-    sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = _native.launch_count()
     barrier()
+    t_begin = time.perf_counter()
     for i in range(args.steps):
         flush.zero_()                        # L2 flush between timed iterations (outside the event pair)
         ev[i][0].record()
         step()
         ev[i][1].record()
     barrier()
+    t_end = time.perf_counter()
     launches = _native.launch_count() - launches0
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_begin, t_end)
     kern = prob.profile_read()               # {kernel: (ms_sum, launches, points)} over the timed region
     prob.profile(False)
     ms = [a.elapsed_time(b) for a, b in ev]

@@ -296,6 +296,7 @@ struct BigWorkspace {
     int regD = 0;                         // padded dimension of the register-resident kernels, 0 = shared-memory kernels
     bool ql_local = false;                // scalar QL keeps the tridiagonal in local memory (more resident warps)
     int ql_ctas = 8;                      // ... CTAs of kWarpsBig warps per SM in that mode
+    size_t budget = 0;                    // bytes the workspace may take (from the free HBM, queried when it has to grow)
 };
 
 bool big_eligible(const ProblemView& pv) {
@@ -352,8 +353,9 @@ int launch_big(const ProblemView& pv, BigWorkspace** wsp, const double* chis, in
     // The scalar QL kernel is a serial chain per point (milliseconds per batch of 32 points, whatever the machine
     // load): its cost is amortised only if MANY batches are in flight, so the chunk takes what the card can spare --
     // up to 40 % of the free HBM, at most 48 GiB (B200: 180 GB) -- rather than a fixed few GiB.
-    size_t budget = (size_t)4 << 30;
-    {
+    const long long all_b0 = (B + 31) / 32;
+    if (ws->budget == 0 || (size_t)all_b0 * per_batch > ws->blob_bytes) {      // (re)query only when the buffer would have to grow
+        size_t budget = (size_t)4 << 30;
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
             const size_t avail = free_b + ws->blob_bytes;           // our own blob is reusable
@@ -362,7 +364,9 @@ int launch_big(const ProblemView& pv, BigWorkspace** wsp, const double* chis, in
             if (want > budget) budget = want;
         } else cudaGetLastError();
         if (const char* env = std::getenv("QTET_BIG_WS_GIB")) { const double g = std::atof(env); if (g > 0) budget = (size_t)(g * 1073741824.0); }
+        ws->budget = budget;
     }
+    const size_t budget = ws->budget;
     long long chunk_b = (long long)budget / (long long)per_batch;
     if (chunk_b < 64) chunk_b = 64;
     const long long all_b = (B + 31) / 32;
