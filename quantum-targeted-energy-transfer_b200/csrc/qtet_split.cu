@@ -459,6 +459,18 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) apply_kernel(SplitArgs a) {
         }
         cp_async_wait<0>();
         PHASE_MARK(0);
+#ifdef QTET_KB_ROT_ONLY      // profiling hook (-DQTET_KB_ROT_ONLY=<CTAs per SM>): the rotation replay alone; results are garbage
+        {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < R; ++k)
+#pragma unroll
+                for (int i = 0; i < D; ++i) acc += v[k][i];
+            if (valid && a.loss) a.loss[p] = acc;
+            __syncwarp();
+            continue;
+        }
+#endif
 
         // ---- c = V[0,:] (row 0 lives in lane q = 0, k = 0), eigenvalues and unit phase steps of my indices
         __syncwarp();
@@ -890,7 +902,11 @@ int launch_split(const ProblemView& pv, SplitWorkspace** wsp, const double* chis
             case 4: rc = launch_apply<4, 4, 4, 4>(a, ws->sms, st); break;
             case 8: rc = launch_apply<8, 8, 4, 4>(a, ws->sms, st); break;
             case 16: rc = launch_apply<16, 8, 2, 6>(a, ws->sms, st); break;
+#ifdef QTET_KB_ROT_ONLY
+            case 21: rc = launch_apply<21, 8, 2, QTET_KB_ROT_ONLY>(a, ws->sms, st); break;
+#else
             case 21: rc = launch_apply<21, 8, 2, 4>(a, ws->sms, st); break;
+#endif
             case 24: rc = launch_apply<24, 8, 2, 4>(a, ws->sms, st); break;
             default: rc = launch_apply<32, 16, 2, 4>(a, ws->sms, st); break;
         }

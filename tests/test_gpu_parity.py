@@ -152,6 +152,55 @@ np.savez(sys.argv[1], *[a for t in out for a in t])
             assert np.abs(a - b).max() < 1e-6 * max(1.0, np.abs(b).max())
 
 
+def test_large_d_chunked_workspace_matches_single_chunk():
+    """The large-d path sizes its workspace from the free HBM; QTET_BIG_WS_GIB=0.25 forces several chunks per call.
+    Chunked and unchunked evaluation must agree bit for bit (same kernels, same points)."""
+    import subprocess
+    import sys
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = f"""
+import sys, numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'quantum-targeted-energy-transfer_b200')!r})
+from tet import _native
+c = {{"max_N": 10, "sites": 3, "max_t": 25, "omegas": [-3, 3, 3], "chis": [0, 0, 0], "coupling": 1, "timesteps": 30}}
+X = np.random.default_rng(21).uniform(-10, 10, (9000, 3))
+p = _native.Problem.from_const(c)
+L, g, k = p.loss_grad_host(X, 2)
+tr = p.trace(X[:700], 0).cpu().numpy()
+np.savez(sys.argv[1], L=L, g=g, k=k, tr=tr)
+"""
+    res = []
+    for env in ({}, {"QTET_BIG_WS_GIB": "0.25"}):          # 0.25 GiB / 3.6 MB per batch -> ~70 batches = 2240 points per chunk
+        with tempfile.NamedTemporaryFile(suffix=".npz") as fh:
+            out = subprocess.run([sys.executable, "-c", code, fh.name], env={**os.environ, **env}, capture_output=True, text=True, timeout=900)
+            assert out.returncode == 0, out.stderr[-2000:]
+            z = np.load(fh.name)
+            res.append({k: z[k] for k in z.files})
+    for key in ("L", "g", "k", "tr"):
+        assert np.array_equal(res[0][key], res[1][key]), key
+    N = 10
+    assert np.all(res[0]["L"] > -1e-9) and np.all(res[0]["L"] < N + 1e-9)
+
+
+def test_large_d_conservation_at_scale(native):
+    """BASELINE configs 3/4 shapes (reduced batch): boson-number conservation sum_k <n_k(t)> = N and <n_0(0)> = N."""
+    for N, om, B in ((10, (-3, 3, 3), 1 << 15), (100, (-3, 3), 1 << 13)):
+        c = make_const(N, om)
+        X = np.random.default_rng(N).uniform(-10, 10, (B, len(om)))
+        prob = native.Problem.from_const(c)
+        tot = None
+        for site in range(len(om)):
+            tr = prob.trace(X, site)
+            tot = tr if tot is None else tot + tr
+            if site == 0:
+                assert float((tr[:, 0] - N).abs().max()) < 1e-9 * N
+        assert float((tot - N).abs().max()) < 2e-8 * max(1, N / 10)
+        loss, grad, ts = prob.loss_grad(X)
+        assert bool((loss > -1e-9).all()) and bool((loss < N + 1e-9).all()) and bool(grad.isfinite().all())
+        prob.close()
+
+
 def test_golden_reference_vectors(native, golden):
     # values produced by the reference's own HamiltonianLoss.py (c128 stand-in arithmetic)
     for r in golden["loss"]:
