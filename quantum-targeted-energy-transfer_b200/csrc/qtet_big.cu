@@ -18,6 +18,9 @@ namespace qtet {
 namespace {
 
 constexpr double kEps = 1.1102230246251565e-16;
+// Pass 1 only supplies shifts: an eigenvalue taken when its off-diagonal is below 2^-33 relative is still accurate to
+// ~e^2/gap (second order), and the looser test saves a quarter of pass 1's rotations (tools/ql_count.py).
+constexpr double kEpsPass1 = kEps * 1048576.0;
 constexpr int kWarpsBig = 2;
 
 struct Mask128 {
@@ -88,12 +91,12 @@ struct QlLaneBig {
     int d;
     __device__ __forceinline__ double& dg(int k) { if constexpr (LOCAL) return ld[k]; else return arr[64 * k]; }
     __device__ __forceinline__ double& of(int k) { if constexpr (LOCAL) return lo[k]; else return arr[64 * k + 32]; }
-    __device__ __forceinline__ Mask128 scan_small() {
+    __device__ __forceinline__ Mask128 scan_small(double eps = kEps) {
         Mask128 m;
         m.set(d - 1);
         for (int k = 0; k < d - 1; ++k) {
             const double dd = fabs(dg(k)) + fabs(dg(k + 1));
-            if (fabs(of(k)) <= kEps * dd) m.set(k);
+            if (fabs(of(k)) <= eps * dd) m.set(k);
         }
         return m;
     }
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(kWarpsBig * 32) ql_scalar_big_kernel(BigQlArgs
             for (int m = 0; m < d; ++m) t.dg(m) -= mean;
             if (pass == 1) break;
             // ---- pass 1: eigenvalues only (plain implicit QL, Wilkinson shifts)
-            Mask128 small = t.scan_small();
+            Mask128 small = t.scan_small(kEpsPass1);
             int l = 0, iter = 0;
             while (true) {
                 const int lnew = small.first_clear_ge(l, d - 1);
@@ -182,15 +185,15 @@ __global__ void __launch_bounds__(kWarpsBig * 32) ql_scalar_big_kernel(BigQlArgs
                     t.dg(i + 1) = dnew;
                     g = fma(c, rr, -bo);
                     t.of(i + 1) = r;                           // of(m) is reset below
-                    put_bit(small, fb, r <= kEps * (fabs(dnew) + fabs(dnext)));
+                    put_bit(small, fb, r <= kEpsPass1 * (fabs(dnew) + fabs(dnext)));
                     fb.down();
                     dnext = dnew; d_hi = d_i; d_i = d_n; e_i = e_n;
                 }
-                if (broke) { small = t.scan_small(); continue; }
+                if (broke) { small = t.scan_small(kEpsPass1); continue; }
                 const double dlnew = d_hi - pp;                // d_hi = dg(l) after the last plane
                 t.dg(l) = dlnew; t.of(l) = g; t.of(m) = 0.0;
                 small.set(m);
-                small.put(l, fabs(g) <= kEps * (fabs(dlnew) + fabs(dnext)));
+                small.put(l, fabs(g) <= kEpsPass1 * (fabs(dlnew) + fabs(dnext)));
             }
             for (int m = 0; m < d; ++m) lam[m] = t.dg(m);
         }
