@@ -374,23 +374,30 @@ int launch_big(const ProblemView& pv, BigWorkspace** wsp, const double* chis, in
     if (chunk_b < 64) chunk_b = 64;
     const long long all_b = (B + 31) / 32;
     if (chunk_b > all_b) chunk_b = all_b;
-    const long long chunk = chunk_b * 32;
     auto align = [](size_t x) { return (x + 255) / 256 * 256; };
-    const size_t o_hdr = align((size_t)chunk_b * ws->capit * 32 * sizeof(double2));
-    const size_t o_it0 = o_hdr + align((size_t)chunk_b * ws->maxr * 32 * 4);
-    const size_t o_nr = o_it0 + align((size_t)chunk_b * ws->maxr * 4);
-    const size_t o_ev = o_nr + align((size_t)chunk_b * 4);
-    const size_t o_list = o_ev + align((size_t)chunk * d * 8);
-    const size_t o_trid = o_list + align((size_t)chunk * 4);
-    const size_t o_trie = o_trid + (dense ? align((size_t)chunk * d * 8) : 0);
-    const size_t o_q = o_trie + (dense ? align((size_t)chunk * d * 8) : 0);
-    const size_t total = o_q + (dense ? align((size_t)chunk * d * d * 8) : 0);
-    if (total > ws->blob_bytes) {
+    long long chunk = 0;
+    size_t o_hdr = 0, o_it0 = 0, o_nr = 0, o_ev = 0, o_list = 0, o_trid = 0, o_trie = 0, o_q = 0, total = 0;
+    while (true) {
+        chunk = chunk_b * 32;
+        o_hdr = align((size_t)chunk_b * ws->capit * 32 * sizeof(double2));
+        o_it0 = o_hdr + align((size_t)chunk_b * ws->maxr * 32 * 4);
+        o_nr = o_it0 + align((size_t)chunk_b * ws->maxr * 4);
+        o_ev = o_nr + align((size_t)chunk_b * 4);
+        o_list = o_ev + align((size_t)chunk * d * 8);
+        o_trid = o_list + align((size_t)chunk * 4);
+        o_trie = o_trid + (dense ? align((size_t)chunk * d * 8) : 0);
+        o_q = o_trie + (dense ? align((size_t)chunk * d * 8) : 0);
+        total = o_q + (dense ? align((size_t)chunk * d * d * 8) : 0);
+        if (total <= ws->blob_bytes) break;
         if (ws->blob) { cudaDeviceSynchronize(); cudaFree(ws->blob); }
         ws->blob = nullptr; ws->blob_bytes = 0;
-        cudaError_t e = cudaMalloc(&ws->blob, total);
-        if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(large-d workspace) failed"); return QTET_ENOMEM; }
-        ws->blob_bytes = total;
+        if (cudaMalloc(&ws->blob, total) == cudaSuccess) { ws->blob_bytes = total; break; }
+        cudaGetLastError();
+        ws->blob = nullptr;
+        // the card cannot spare that much (fragmentation, other tenants): halve the chunk and remember the smaller budget
+        if (chunk_b <= 64) { set_error("cudaMalloc(large-d workspace) failed"); return QTET_ENOMEM; }
+        chunk_b = (chunk_b / 2 < 64) ? 64 : chunk_b / 2;
+        ws->budget = (size_t)chunk_b * per_batch;
     }
     BigStream bs;
     bs.stream = (double2*)ws->blob; bs.hdr = (unsigned*)(ws->blob + o_hdr); bs.it0 = (int*)(ws->blob + o_it0);
