@@ -41,7 +41,7 @@ def build(force=False, verbose=False):
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "qtet.h"))
-    objs = []
+    objs, jobs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
@@ -51,7 +51,13 @@ def build(force=False, verbose=False):
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), flush=True)
-            subprocess.run(cmd, check=True)
+            jobs.append(cmd)
+    if jobs:                                   # the translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:
+            for r in pool.map(lambda c: subprocess.run(c, check=False), jobs):
+                if r.returncode:
+                    raise subprocess.CalledProcessError(r.returncode, r.args)
     if force or _stale(LIB, objs):
         cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs]
         if verbose:
