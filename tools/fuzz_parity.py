@@ -1,0 +1,39 @@
+#!/usr/bin/env python3
+"""Randomised parity sweep: random systems (sites, N, omegas, coupling, max_t, timesteps) and points, CUDA path vs oracle.
+    python tools/fuzz_parity.py [n_cases] [seed]"""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "quantum-targeted-energy-transfer_b200"))
+from tet import _native
+from oracle import qtet_oracle as O
+
+n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+worst = (0.0, 0.0, None)
+for case in range(n_cases):
+    f = int(rng.choice([2, 2, 3, 3, 4]))
+    N = int(rng.integers(1, {2: 64, 3: 11, 4: 6}[f] + 1))
+    om = [float(x) for x in np.round(rng.uniform(-4, 4, f), 2)]
+    const = {"max_N": N, "sites": f, "max_t": int(rng.integers(1, 40)), "omegas": om, "chis": [0] * f,
+             "coupling": float(np.round(rng.uniform(-3, 3), 2)), "timesteps": int(rng.choice([1, 2, 7, 16, 17, 30, 33, 64]))}
+    B = int(rng.choice([1, 5, 33, 70]))
+    X = rng.uniform(-10, 10, (B, f)) * rng.choice([1.0, 0.1, 0.0], p=[0.8, 0.15, 0.05])
+    site = int(rng.integers(0, f))
+    prob = _native.Problem.from_const(const)
+    L, g, k = [t.cpu().numpy() for t in prob.loss_grad(X, site)]
+    tr = prob.trace(X, site).cpu().numpy()
+    prob.close()
+    Lr, gr, kr = O.loss_grad_batch(const, X, site)
+    trr = O.trace(const, X, site)
+    scale = max(1.0, N) * (1.0 + 1e-3 * N * N * const["max_t"])
+    dl = np.abs(L - Lr).max() / scale
+    dt = np.abs(tr - trr).max() / scale
+    same = k == kr
+    dg = (np.abs(g - gr) / np.maximum(1.0, np.abs(gr).max(axis=1, keepdims=True)))[same].max() if same.any() else 0.0
+    ok = dl < 1e-9 and dt < 1e-9 and dg < 1e-6 * (1 + N) and np.isfinite(L).all() and np.isfinite(g).all() and same.mean() > 0.9
+    if max(dl, dt) > worst[0]: worst = (max(dl, dt), dg, const)
+    if not ok:
+        print("FAIL", const, "B", B, "site", site, "dloss", dl, "dtrace", dt, "dgrad", dg, "same_t", same.mean())
+        sys.exit(1)
+print(f"{n_cases} random cases ok; worst scaled loss/trace error {worst[0]:.2e} (grad {worst[1]:.2e}) at {worst[2]}")
