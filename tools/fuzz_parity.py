@@ -30,8 +30,12 @@ for case in range(n_cases):
     dl = np.abs(L - Lr).max() / scale
     dt = np.abs(tr - trr).max() / scale
     same = k == kr
+    if not same.all():                       # a different arg-max sample is fine on a numerical tie of the two samples
+        idx = np.arange(len(k))[~same]
+        tie = np.abs(trr[idx, k[~same]] - trr[idx, kr[~same]]) <= 1e-9 * scale
+        assert tie.all(), ("t* differs without a tie", const)
     dg = (np.abs(g - gr) / np.maximum(1.0, np.abs(gr).max(axis=1, keepdims=True)))[same].max() if same.any() else 0.0
-    ok = dl < 1e-9 and dt < 1e-9 and dg < 1e-6 * (1 + N) and np.isfinite(L).all() and np.isfinite(g).all() and same.mean() > 0.9
+    ok = dl < 1e-9 and dt < 1e-9 and dg < 1e-6 * (1 + N) and np.isfinite(L).all() and np.isfinite(g).all()
     if max(dl, dt) > worst[0]: worst = (max(dl, dt), dg, const)
     if not ok:
         print("FAIL", const, "B", B, "site", site, "dloss", dl, "dtrace", dt, "dgrad", dg, "same_t", same.mean())
