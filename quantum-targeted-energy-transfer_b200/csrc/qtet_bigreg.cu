@@ -29,7 +29,17 @@ constexpr int kRingR = 4;      // trips of (c, s) in flight per CTA (cp.async ri
 #define QTET_FUSE 2
 #endif
 constexpr int kFuse = QTET_FUSE;   // QL rounds replayed together per trip
-constexpr int kTC = 16;        // time samples per evolution chunk
+[[maybe_unused]] constexpr int kTC = 16;        // time samples per evolution chunk (DFMA evolution)
+#ifndef QTET_EVO_MMA
+#define QTET_EVO_MMA 1         // 1: time evolution psi = V z on the FP64 tensor path (mma.sync m8n8k4), 0: DFMA loop with broadcast z
+#endif
+constexpr int kNC = 16;        // real columns (= 8 time samples x re|im) per DMMA evolution chunk
+
+// D(8x8) += A(8x4, row) B(4x8, col) in FP64: lane l holds A[l/4][l%4], B[l%4][l/4], C[l/4][2(l%4) .. +1]
+__device__ __forceinline__ void dmma884(double2& c, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c.x), "+d"(c.y) : "d"(a), "d"(b));
+}
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -45,6 +55,11 @@ __device__ __forceinline__ unsigned smem_addr(const void* p) {
     unsigned a = (unsigned)__cvta_generic_to_shared(p);
     asm volatile("" : "+r"(a));
     return a;
+}
+__device__ __forceinline__ double lds64(unsigned addr) {
+    double r;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(addr));
+    return r;
 }
 __device__ __forceinline__ double2 lds128(unsigned addr) {
     double2 r;
@@ -349,7 +364,11 @@ template <int D, int NW>
 struct RpLayout {
     static constexpr int NT = NW * 32;
     static constexpr int DP = (D + 1) & ~1;
-    static constexpr int LDV = D | 1;
+    static constexpr int KP = (D + 3) & ~3;                  // eigen-index range padded to the DMMA k step
+    static constexpr int LDV = KP | 1;                       // odd: row stores and column reads are conflict-free
+    static constexpr int LDZ = KP + ((4 - KP % 16) + 16) % 16;   // = 4 (mod 16): a B fragment load takes its minimum of 2 wavefronts
+    static constexpr int MT = (D + 7) / 8;                   // DMMA row tiles
+    static constexpr int MTW = (MT + NW - 1) / NW;           // ... per warp (tile mt belongs to warp mt % NW)
     static constexpr int NP = D * (D - 1) / 2;
     // always live (doubles)
     static constexpr int VEC = 0;                            // [8][DP]  e, c, fr, fi, ar, ai, br, bi
@@ -360,9 +379,18 @@ struct RpLayout {
     static constexpr int RING = 0;                           // double2 [kRingR][kFuse][DP]   (c, s) by plane index
     static constexpr int R1 = kRingR * kFuse * DP * 2;       // followed by uint2 hdr[maxr] (runtime size)
     // evolution phase
+#if QTET_EVO_MMA
+    static constexpr int ZM = (D * LDV + 1) & ~1;                     // behind V (VSM below): double [kNC][LDZ], column n = (sample, re|im)
+    static constexpr int PARTM = ZM + kNC * LDZ;             // [NW][kNC / 2]
+    static constexpr int R2 = PARTM + NW * (kNC / 2);
+    static constexpr int ZT = ZM;                            // psi(t*) broadcast buffer (double2 [DP]) once the evolution is over
+    static_assert(kNC * LDZ >= 2 * DP, "psi* buffer must fit the Z chunk");
+    static_assert(NT >= KP, "every padded eigen-index needs a thread");
+#else
     static constexpr int ZT = 0;                             // double2 [kTC][DP]
     static constexpr int PART = ZT + kTC * DP * 2;           // [kTC][NT + 1]
     static constexpr int R2 = PART + kTC * (NT + 1);
+#endif
     // gradient phase
     static constexpr int VSM = 0;                            // [D][LDV], then S: [DP diag][NP pairs]
     static constexpr int R3a = D * LDV;
@@ -401,7 +429,12 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) replay
     int2* tw = reinterpret_cast<int2*>(ph + L::R1 + a.bs.maxr);     // per-trip windows, behind the headers
     const unsigned ring_a = smem_addr(ring);
     double2* zt = reinterpret_cast<double2*>(ph + L::ZT);
+#if QTET_EVO_MMA
+    double* zm = ph + L::ZM;
+    double* partm = ph + L::PARTM;
+#else
     double* part = ph + L::PART;
+#endif
     double* vsm = ph + L::VSM;
     double* sp = ph + L::VSM;
     // tr[T] sits behind the largest phase region (runtime offset handed in through the launch: bs.maxr bounds hs)
@@ -565,6 +598,92 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) replay
             wim = -fma(cs_, lo, sn);
             zr = ci;
         }
+#if QTET_EVO_MMA
+        // ---- time evolution on the FP64 tensor path: P[row][n] = sum_i V[row][i] Z[i][n], n = (sample, re|im), as
+        // m8n8k4 DMMAs with V (parked in shared memory once -- the gradient needs it there anyway) as the A operand and
+        // the phase table Z of a chunk of 8 samples as B.  A C fragment holds (re, im) of psi_row(t_s) in one lane,
+        // so |psi|^2 is lane-local; the weighted sum over rows is three shuffles and one partial per warp.
+        {
+            constexpr int KP = L::KP, LDZ = L::LDZ, MTW = L::MTW;
+            if (row < d) {
+#pragma unroll
+                for (int i = 0; i < D; ++i) vsm[(size_t)row * LDV + i] = v[i];
+#pragma unroll
+                for (int i = D; i < KP; ++i) vsm[(size_t)row * LDV + i] = 0.0;
+            }
+            // (v is reloaded from shared memory after the evolution, so its registers are free for the DMMA loop)
+            const int lg = lane >> 2, lt = lane & 3;
+            unsigned aaddr[MTW];                             // A fragment base of my row tiles (rows >= d: clamped, weight 0)
+            double wrow[MTW];
+            int nmt = 0;                                     // my tiles are warp, warp + NW, ...: the valid ones are a prefix
+#pragma unroll
+            for (int m = 0; m < MTW; ++m) {
+                const int r = 8 * (warp + m * NW) + lg;
+                const int rc = (r < d) ? r : (d - 1);
+                aaddr[m] = smem_addr(vsm) + (unsigned)((rc * LDV + lt) * 8);
+                wrow[m] = (r < d) ? pv.occ[r * f + a.site] : 0.0;
+                if (8 * (warp + m * NW) < d) nmt = m + 1;
+            }
+            const unsigned baddr = smem_addr(zm) + (unsigned)((lg * LDZ + lt) * 8);
+            for (int k0 = 0; k0 < T; k0 += kNC / 2) {
+                __syncthreads();                             // V is in place / the previous chunk is consumed
+                if (row < KP) {
+#pragma unroll
+                    for (int kk = 0; kk < kNC / 2; ++kk) {
+                        zm[(size_t)(2 * kk) * LDZ + row] = zr;
+                        zm[(size_t)(2 * kk + 1) * LDZ + row] = zi;
+                        const double nr_ = fma(zr, wre, -(zi * wim));
+                        zi = fma(zr, wim, zi * wre);
+                        zr = nr_;
+                    }
+                }
+                __syncthreads();
+                double2 acc[MTW][kNC / 8];
+#pragma unroll
+                for (int m = 0; m < MTW; ++m)
+#pragma unroll
+                    for (int n = 0; n < kNC / 8; ++n) acc[m][n] = make_double2(0.0, 0.0);
+                // the tile count is warp-uniform: one branch-free k loop per possible count
+                static_for<MTW>([&](auto Cc) {
+                    constexpr int NMT = decltype(Cc)::value + 1;
+                    if (nmt == NMT) {
+#pragma unroll 4
+                        for (int ks = 0; ks < KP; ks += 4) {
+                            double bf[kNC / 8], af[NMT];
+#pragma unroll
+                            for (int n = 0; n < kNC / 8; ++n) bf[n] = lds64(baddr + (unsigned)((8 * n * LDZ + ks) * 8));
+#pragma unroll
+                            for (int m = 0; m < NMT; ++m) af[m] = lds64(aaddr[m] + (unsigned)(ks * 8));
+#pragma unroll
+                            for (int m = 0; m < NMT; ++m)
+#pragma unroll
+                                for (int n = 0; n < kNC / 8; ++n) dmma884(acc[m][n], af[m], bf[n]);
+                        }
+                    }
+                });
+#pragma unroll
+                for (int n = 0; n < kNC / 8; ++n) {
+                    double sum = 0.0;
+#pragma unroll
+                    for (int m = 0; m < MTW; ++m) sum = fma(wrow[m], fma(acc[m][n].x, acc[m][n].x, acc[m][n].y * acc[m][n].y), sum);
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+                    if (lane < 4) partm[warp * (kNC / 2) + 4 * n + lane] = sum;      // sample 4 n + lane of the chunk
+                }
+                __syncthreads();
+                if (tid < kNC / 2 && k0 + tid < T) {
+                    double s0 = 0.0;
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) s0 += partm[w * (kNC / 2) + tid];
+                    tr[k0 + tid] = s0;
+                }
+            }
+            // my row of V back into registers (rows >= d are padding: zero)
+#pragma unroll
+            for (int i = 0; i < D; ++i) v[i] = (row < d) ? vsm[(size_t)row * LDV + i] : 0.0;
+        }
+#else
         // ---- time evolution in chunks of kTC samples
         for (int k0 = 0; k0 < T; k0 += kTC) {
             if (row < D) {
@@ -602,6 +721,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) replay
                 tr[k0 + tid] = s0 + s1;
             }
         }
+#endif
         __syncthreads();
         BPHASE_MARK(6);
         if (a.trace != nullptr)
@@ -651,11 +771,13 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) replay
             }
             wv[row] = make_double2(wsite * (pr0 + pr1), -wsite * (pi0 + pi1));
         }
+#if !QTET_EVO_MMA
         __syncthreads();                                 // zt is dead: V goes to shared memory for the column sums
         if (row < d) {
 #pragma unroll
             for (int i = 0; i < D; ++i) vsm[(size_t)row * LDV + i] = v[i];
         }
+#endif
         __syncthreads();
         if (row < D) {
             double ar = 0.0, ai = 0.0;
