@@ -49,7 +49,6 @@ struct SplitArgs {
     double* ev;               // [n, d]  eigenvalues (shifted by the mean of the diagonal)
     int* overflow_list;       // [n]
     int* overflow_count;      // [1]
-    const unsigned short* pair_tab;   // [D(D-1)/2] i | j << 8
     double* loss; double* grad; int* tstar; double* trace;   // chunk-offset outputs
 };
 
@@ -325,7 +324,8 @@ struct BLayout {
     static constexpr int NCOPY = (NPL + kTail + ROWS_PER_COPY - 1) / ROWS_PER_COPY;
     static constexpr int SLOT_ROWS = 2 * NPL + kTail;  // [NPL identity guard rows][NPL + kTail data rows]
     static constexpr int DH = (D + 1) / 2;             // half of the eigen-indices (a-reduction in two halves)
-    static constexpr int NP = D * (D - 1) / 2;         // index pairs i < j
+    static constexpr int HH = D / 2;                   // cyclic offsets per eigen-index: the pair {i, (i + o) mod D}, o = 1 .. HH
+    static constexpr int NP = D * HH;                  // ... covers every index pair once (even D: o = D/2 only for i < D/2)
     // shared memory per warp, in doubles
     static constexpr int RING = kRing * SLOT_ROWS * PPW * 2;           // double2 [kRing][SLOT_ROWS][PPW]
     static constexpr int HDR = kMaxRounds * PPW / 2;                   // unsigned [kMaxRounds][PPW]
@@ -363,9 +363,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) apply_kernel(SplitArgs a) {
     double2* zbuf = reinterpret_cast<double2*>(base + L::PHASED);            // [2][PPW][D]
     double* cbuf = base + L::PHASED + L::ZB;                                 // [PPW][D]
 
-    __shared__ unsigned short s_pair[NP > 0 ? NP : 1];
-    for (int i = threadIdx.x; i < NP; i += blockDim.x) s_pair[i] = a.pair_tab[i];
-    __syncthreads();
     const double dt = (T > 1) ? pv.tgrid[1] : 0.0;
     double wsite[R];
 #pragma unroll
@@ -642,47 +639,56 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) apply_kernel(SplitArgs a) {
         }
         __syncwarp();
         PHASE_MARK(9);
-        // S_ij = K_ij + K_ji for i < j; pairs dealt round-robin to the G lanes of the point, four pairs in
-        // flight per lane (independent load -> reciprocal -> product chains), rare near-degenerate pairs fixed up
-        // afterwards.
-        for (int q0 = q; q0 < NP; q0 += 4 * G) {
-            int pi_[4], pj_[4];
-            double dl[4], kd[4];
+        // S_ij = K_ij + K_ji.  Lane q pairs each of its own eigen-indices i (whose e, c, f, a, b it holds in registers)
+        // with j = (i + o) mod D, o = 1 .. D/2: every index pair exactly once, the partner's values are read from
+        // consecutive addresses by the lanes of a point (no table look-up, no gather), and S lands in the order
+        // [i][o] the row sums below walk through with static indices.
+        {
+            constexpr int HH = L::HH, U = 5;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int qq = q0 + u * G;
-                const unsigned ij = s_pair[(qq < NP) ? qq : 0];
-                pi_[u] = ij & 0xff; pj_[u] = ij >> 8;
-            }
+            for (int t = 0; t < RZ; ++t) {
+                const int i = q + t * G;
+                if (i < D) {
+                    const double e_i = ei[t], c_i = ci[t], fr_i = fr[t], fi_i = fi[t], ar_i = ar[t], ai_i = ai[t];
+                    const double br_i = fma(ar_i, fr_i, -(ai_i * fi_i));
+                    const int omax = ((D & 1) || i < D / 2) ? HH : HH - 1;
+#pragma unroll 1
+                    for (int o0 = 1; o0 <= omax; o0 += U) {
+                        double dl[U], kd[U];
+                        int jj[U];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = pi_[u], j = pj_[u];
-                dl[u] = lvp[i] - lvp[j];
-                // K_ij = c_j R (br_i - ar_i fr_j + ai_i fi_j) ; K_ji = -c_i R (br_j - ar_j fr_i + ai_j fi_i)
-                const double kij = lvp[PPW * D + j] * (lvp[6 * PPW * D + i] - lvp[4 * PPW * D + i] * lvp[2 * PPW * D + j] + lvp[5 * PPW * D + i] * lvp[3 * PPW * D + j]);
-                const double kji = lvp[PPW * D + i] * (lvp[6 * PPW * D + j] - lvp[4 * PPW * D + j] * lvp[2 * PPW * D + i] + lvp[5 * PPW * D + j] * lvp[3 * PPW * D + i]);
-                kd[u] = kij - kji;
-            }
+                        for (int u = 0; u < U; ++u) {
+                            int j = i + ((o0 + u <= omax) ? (o0 + u) : omax);
+                            if (j >= D) j -= D;
+                            jj[u] = j;
+                            dl[u] = e_i - lvp[j];
+                            // K_ij = c_j (br_i - ar_i fr_j + ai_i fi_j) ; K_ji = c_i (br_j - ar_j fr_i + ai_j fi_i)
+                            const double kij = lvp[PPW * D + j] * (br_i - ar_i * lvp[2 * PPW * D + j] + ai_i * lvp[3 * PPW * D + j]);
+                            const double kji = c_i * (lvp[6 * PPW * D + j] - lvp[4 * PPW * D + j] * fr_i + lvp[5 * PPW * D + j] * fi_i);
+                            kd[u] = kij - kji;
+                        }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) kd[u] *= fast_rcp(dl[u]);
+                        for (int u = 0; u < U; ++u) kd[u] *= fast_rcp(dl[u]);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int qq = q0 + u * G;
-                if (qq < NP) {
-                    double sij = kd[u];
-                    if (fabs(dl[u] * ts) < 1e-2) {
-                        // near-degenerate: Phi_ij = ts f_j (exp(-i x) - 1)/x ; S = Re[(a_i c_j + a_j c_i) Phi_ij]
-                        const int i = pi_[u], j = pj_[u];
-                        double gr, gi;
-                        expm1_over_x(dl[u] * ts, gr, gi);
-                        const double fjr = lvp[2 * PPW * D + j], fji = lvp[3 * PPW * D + j];
-                        const double phr = ts * (fjr * gr - fji * gi), phi = ts * (fjr * gi + fji * gr);
-                        const double c_i = lvp[PPW * D + i], c_j = lvp[PPW * D + j];
-                        const double mr = lvp[4 * PPW * D + i] * c_j + lvp[4 * PPW * D + j] * c_i;
-                        const double mi = lvp[5 * PPW * D + i] * c_j + lvp[5 * PPW * D + j] * c_i;
-                        sij = mr * phr - mi * phi;
+                        for (int u = 0; u < U; ++u) {
+                            if (o0 + u <= omax) {
+                                double sij = kd[u];
+                                if (fabs(dl[u] * ts) < 1e-2) {
+                                    // near-degenerate: Phi_ij = ts f_j (exp(-i x) - 1)/x ; S = Re[(a_i c_j + a_j c_i) Phi_ij]
+                                    const int j = jj[u];
+                                    double gr, gi;
+                                    expm1_over_x(dl[u] * ts, gr, gi);
+                                    const double fjr = lvp[2 * PPW * D + j], fji = lvp[3 * PPW * D + j];
+                                    const double phr = ts * (fjr * gr - fji * gi), phi = ts * (fjr * gi + fji * gr);
+                                    const double c_j = lvp[PPW * D + j];
+                                    const double mr = ar_i * c_j + lvp[4 * PPW * D + j] * c_i;
+                                    const double mi = ai_i * c_j + lvp[5 * PPW * D + j] * c_i;
+                                    sij = mr * phr - mi * phi;
+                                }
+                                sp[D + i * HH + (o0 + u - 1)] = sij;
+                            }
+                        }
                     }
-                    sp[D + qq] = sij;
                 }
             }
         }
@@ -692,7 +698,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) apply_kernel(SplitArgs a) {
 #pragma unroll
         for (int kk = 0; kk < R; ++kk) Gm[kk] = 0.0;
         {
-            int qq = 0;
+            constexpr int HH = L::HH;
 #pragma unroll
             for (int i = 0; i < D; ++i) {
                 const double kd = sp[i];
@@ -700,11 +706,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) apply_kernel(SplitArgs a) {
 #pragma unroll
                 for (int kk = 0; kk < R; ++kk) acc[kk] = kd * v[kk][i];
 #pragma unroll
-                for (int j = i + 1; j < D; ++j) {
-                    const double sv = sp[D + qq];
-                    ++qq;
+                for (int o = 1; o <= HH; ++o) {
+                    if ((D & 1) || o < HH || i < D / 2) {
+                        const int j = (i + o) % D;
+                        const double sv = sp[D + i * HH + (o - 1)];
 #pragma unroll
-                    for (int kk = 0; kk < R; ++kk) acc[kk] = fma(sv, v[kk][j], acc[kk]);
+                        for (int kk = 0; kk < R; ++kk) acc[kk] = fma(sv, v[kk][j], acc[kk]);
+                    }
                 }
 #pragma unroll
                 for (int kk = 0; kk < R; ++kk) Gm[kk] = fma(v[kk][i], acc[kk], Gm[kk]);
@@ -762,7 +770,6 @@ struct SplitWorkspace {
     long long chunk = 0;
     char* blob = nullptr;            // two chunk buffers (double-buffered between K_A and K_B)
     size_t blob_bytes = 0;
-    unsigned short* pair_tab = nullptr;
     int* overflow_count = nullptr;   // [2]
     cudaStream_t aux = nullptr;      // K_A runs here, one chunk ahead of K_B on the caller's stream
     cudaEvent_t ev_fork = nullptr, ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr};
@@ -783,7 +790,6 @@ bool split_eligible(const ProblemView& pv) {
 void split_workspace_free(SplitWorkspace* ws) {
     if (!ws) return;
     if (ws->blob) cudaFree(ws->blob);
-    if (ws->pair_tab) cudaFree(ws->pair_tab);
     if (ws->overflow_count) cudaFree(ws->overflow_count);
     if (ws->aux) cudaStreamDestroy(ws->aux);
     if (ws->ev_fork) cudaEventDestroy(ws->ev_fork);
@@ -816,12 +822,6 @@ int launch_split(const ProblemView& pv, SplitWorkspace** wsp, const double* chis
             const int v = std::atoi(env);
             if (v > 0 && v < ws->capit) ws->capit = v;
         }
-        std::vector<unsigned short> tab;
-        for (int i = 0; i < ws->D; ++i)
-            for (int j = i + 1; j < ws->D; ++j) tab.push_back((unsigned short)(i | (j << 8)));
-        if (tab.empty()) tab.push_back(0);
-        QTET_CUDA(cudaMalloc(&ws->pair_tab, tab.size() * sizeof(unsigned short)));
-        QTET_CUDA(cudaMemcpy(ws->pair_tab, tab.data(), tab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
         QTET_CUDA(cudaMalloc(&ws->overflow_count, 2 * sizeof(int)));
         QTET_CUDA(cudaStreamCreateWithFlags(&ws->aux, cudaStreamNonBlocking));
         QTET_CUDA(cudaEventCreateWithFlags(&ws->ev_fork, cudaEventDisableTiming));
@@ -858,7 +858,6 @@ int launch_split(const ProblemView& pv, SplitWorkspace** wsp, const double* chis
 
     SplitArgs a;
     a.pv = pv; a.site = site; a.acceptor = (site == pv.f - 1) ? 1 : 0; a.capit = ws->capit;
-    a.pair_tab = ws->pair_tab;
 
     const size_t smemA = (size_t)kWarpsA * 2 * d * 32 * sizeof(double);
     QTET_CUDA(cudaFuncSetAttribute(ql_scalar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
