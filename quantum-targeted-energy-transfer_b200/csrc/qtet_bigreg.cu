@@ -33,6 +33,9 @@ constexpr int kFuse = QTET_FUSE;   // QL rounds replayed together per trip
 #ifndef QTET_EVO_MMA
 #define QTET_EVO_MMA 1         // 1: time evolution psi = V z on the FP64 tensor path (mma.sync m8n8k4), 0: DFMA loop with broadcast z
 #endif
+#ifndef QTET_S_CYCLIC
+#define QTET_S_CYCLIC 1        // storage order of the pair kernel S: 1 = [i][o] (cyclic offsets), 0 = packed upper triangle
+#endif
 constexpr int kNC = 16;        // real columns (= 8 time samples x re|im) per DMMA evolution chunk
 
 // D(8x8) += A(8x4, row) B(4x8, col) in FP64: lane l holds A[l/4][l%4], B[l%4][l/4], C[l/4][2(l%4) .. +1]
@@ -90,7 +93,7 @@ struct RegArgs {
     long long n;
     int site, acceptor;
     BigStream bs;
-    const unsigned short* pair_tab;   // [D(D-1)/2]  i | j << 8, lexicographic (i, j > i)
+    const unsigned short* pair_tab;   // [D(D-1)/2]  i | j << 8, lexicographic (i, j > i); used by the D <= 66 kernels
     double* loss; double* grad; int* tstar; double* trace;
 };
 
@@ -369,7 +372,13 @@ struct RpLayout {
     static constexpr int LDZ = KP + ((4 - KP % 16) + 16) % 16;   // = 4 (mod 16): a B fragment load takes its minimum of 2 wavefronts
     static constexpr int MT = (D + 7) / 8;                   // DMMA row tiles
     static constexpr int MTW = (MT + NW - 1) / NW;           // ... per warp (tile mt belongs to warp mt % NW)
-    static constexpr int NP = D * (D - 1) / 2;
+    static constexpr int HH = D / 2;                         // cyclic offsets per eigen-index: pair {i, (i + o) mod D}, o = 1 .. HH
+    // Storage / evaluation order of the pair kernel S.  Cyclic ([i][o], partner (i + o) mod D): no gathers in the pair
+    // phase, but every register of V stays live through the row sums; packed upper triangle: V registers die row by
+    // row, which the register-starved D <= 66 kernels (168 registers) need more than the conflict-free loads.
+    static constexpr bool CYC = (QTET_S_CYCLIC != 0) && (D > 66);
+    static constexpr int HHP = (HH + 1) & ~1;                // cyclic: row stride of S (even: every row starts on a 16 B boundary)
+    static constexpr int NP = CYC ? D * HHP : D * (D - 1) / 2;
     // always live (doubles)
     static constexpr int VEC = 0;                            // [8][DP]  e, c, fr, fi, ar, ai, br, bi
     static constexpr int WV = VEC + 8 * DP;                  // double2 [NT]   n_site conj(psi(t*))
@@ -779,6 +788,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) replay
         }
 #endif
         __syncthreads();
+        double ar_ = 0.0, ai_ = 0.0;                       // a_row = sum_j V[j][row] w_j, kept for the pair kernel
         if (row < D) {
             double ar = 0.0, ai = 0.0;
             if (row < d) {
@@ -794,12 +804,60 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) replay
                 ar += ar1; ai += ai1;
             }
             const double bre = fma(ar, fr, -(ai * fi)), bim = fma(ar, fi, ai * fr);
+            ar_ = ar; ai_ = ai;
             vec[0 * DP + row] = ei; vec[1 * DP + row] = ci; vec[2 * DP + row] = fr; vec[3 * DP + row] = fi;
             vec[4 * DP + row] = ar; vec[5 * DP + row] = ai; vec[6 * DP + row] = bre; vec[7 * DP + row] = bim;
         }
         __syncthreads();                                 // V in shared memory is dead: the kernel S takes its place
         BPHASE_MARK(7);
         if (row < D) sp[row] = (row < d) ? ci * ts * vec[7 * DP + row] : 0.0;      // K_ii = c_i t* Im(b_i)
+        // S_ij = K_ij + K_ji.  Thread i pairs its own eigen-index (e, c, f, a, b in registers) with j = (i + o) mod D,
+        // o = 1 .. D/2: every index pair once, the partner's values come from consecutive addresses across the warp
+        // (no pair table, no gather), and S lands in the [i][o] order the row sums below walk through statically.
+        // D <= 66 keeps the packed upper triangle dealt out through the pair table (see RpLayout::CYC).
+        if constexpr (L::CYC) { if (row < D) {
+            constexpr int HH = L::HH, U = 4;
+            const int i = row;
+            const double br_i = fma(ar_, fr, -(ai_ * fi));
+            const int omax = ((D & 1) || i < D / 2) ? HH : HH - 1;
+#pragma unroll 1
+            for (int o0 = 1; o0 <= omax; o0 += U) {
+                double dl[U], kd[U];
+                int jj[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    int j = i + ((o0 + u <= omax) ? (o0 + u) : omax);
+                    if (j >= D) j -= D;
+                    jj[u] = j;
+                    dl[u] = ei - vec[j];
+                    const double kij = vec[DP + j] * (br_i - ar_ * vec[2 * DP + j] + ai_ * vec[3 * DP + j]);
+                    const double kji = ci * (vec[6 * DP + j] - vec[4 * DP + j] * fr + vec[5 * DP + j] * fi);
+                    kd[u] = kij - kji;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) kd[u] *= fast_rcp(dl[u]);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (o0 + u <= omax) {
+                        const int j = jj[u];
+                        double sij = kd[u];
+                        if (i >= d || j >= d) sij = 0.0;
+                        else if (fabs(dl[u] * ts) < 1e-2) {
+                            // near-degenerate: Phi_ij = ts f_j (exp(-i x) - 1)/x ; S = Re[(a_i c_j + a_j c_i) Phi_ij]
+                            double gr, gi;
+                            expm1_over_x(dl[u] * ts, gr, gi);
+                            const double fjr = vec[2 * DP + j], fji = vec[3 * DP + j];
+                            const double phr = ts * (fjr * gr - fji * gi), phi = ts * (fjr * gi + fji * gr);
+                            const double c_j = vec[DP + j];
+                            const double mr = ar_ * c_j + vec[4 * DP + j] * ci;
+                            const double mi = ai_ * c_j + vec[5 * DP + j] * ci;
+                            sij = mr * phr - mi * phi;
+                        }
+                        sp[DP + i * L::HHP + (o0 + u - 1)] = sij;
+                    }
+                }
+            }
+        } } else {
         // S_ij = K_ij + K_ji for i < j
         for (int q0 = tid; q0 < NP; q0 += 2 * NT) {
             int pi_[2], pj_[2];
@@ -842,6 +900,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) replay
                 }
             }
         }
+        }
         __syncthreads();
         BPHASE_MARK(8);
         // G_row = 2 [sum_i K_ii V_i^2 + sum_{i<j} S_ij V_i V_j], every index static
@@ -849,6 +908,23 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) replay
         {
             const double2* sp2 = reinterpret_cast<const double2*>(sp + DP);
             double2 cur = make_double2(0.0, 0.0);
+            if constexpr (L::CYC) {
+            static_for<D>([&](auto Ic) {
+                constexpr int i = decltype(Ic)::value;
+                constexpr int HH = L::HH;
+                constexpr int no = ((D & 1) || i < D / 2) ? HH : HH - 1;        // offsets of index i
+                double acc0 = sp[i] * v[i], acc1 = 0.0;
+                static_for<no>([&](auto Oc) {
+                    constexpr int o = 1 + decltype(Oc)::value;
+                    constexpr int j = (i + o) % D;
+                    constexpr int qq = i * L::HHP + (o - 1);                // rows start on even entries: read in pairs
+                    double sv;
+                    if constexpr ((qq & 1) == 0) { cur = sp2[qq >> 1]; sv = cur.x; } else sv = cur.y;
+                    if constexpr ((o & 1) != 0) acc0 = fma(sv, v[j], acc0); else acc1 = fma(sv, v[j], acc1);
+                });
+                Gm = fma(v[i], acc0 + acc1, Gm);
+            });
+            } else {
             static_for<D>([&](auto Ic) {
                 constexpr int i = decltype(Ic)::value;
                 double acc0 = sp[i] * v[i], acc1 = 0.0;
@@ -861,6 +937,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) replay
                 });
                 Gm = fma(v[i], acc0 + acc1, Gm);
             });
+            }
         }
         for (int k = 0; k < f; ++k) {
             const double qk = (row < d) ? pv.quad[row * f + k] : 0.0;
