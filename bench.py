@@ -155,9 +155,19 @@ def _cpu_worker(args):
     const, pts, site = args
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     from oracle import qtet_oracle as O
+    import math
+    d = math.comb(const["max_N"] + const["sites"] - 1, const["sites"] - 1)
+    step = max(8, min(2048, (2048 * 441) // (d * d)))     # keep the batched intermediates ([B, d, d] and up) cache-sized
     out = []
-    for lo in range(0, len(pts), 2048):
-        out.append(O.loss_grad_batch(const, pts[lo:lo + 2048], site)[0])
+    try:                                                  # one BLAS/LAPACK thread per process: the pool already uses every core
+        from threadpoolctl import threadpool_limits
+        guard = threadpool_limits(limits=1)
+    except Exception:
+        guard = None
+    for lo in range(0, len(pts), step):
+        out.append(O.loss_grad_batch(const, pts[lo:lo + step], site)[0])
+    if guard is not None:
+        guard.restore_original_limits()
     return float(np.sum(np.concatenate(out)))
 
 
@@ -167,10 +177,14 @@ def cpu_rate(const, pts, cores, seconds_target=12.0):
     site = const["sites"] - 1
     ctx = mp.get_context("fork")
     # calibrate on one core
-    probe = pts[:min(len(pts), 256)]
+    probe = pts[:min(len(pts), 32)]
     t0 = time.perf_counter(); _cpu_worker((const, probe, site)); t_probe = time.perf_counter() - t0
+    if t_probe < 0.5:                                     # small systems: a longer probe for a usable estimate
+        probe = pts[:min(len(pts), 256)]
+        t0 = time.perf_counter(); _cpu_worker((const, probe, site)); t_probe = time.perf_counter() - t0
     per_core = len(probe) / t_probe
-    n = int(min(len(pts), max(cores * 256, per_core * cores * seconds_target)))
+    # bounded sample: about `seconds_target` of wall time on `cores` processes (at least 8 points per process)
+    n = int(min(len(pts), max(cores * 8, per_core * cores * seconds_target)))
     n -= n % cores
     chunks = np.array_split(pts[:n], cores)
     with ctx.Pool(cores) as pool:
