@@ -350,6 +350,10 @@ def test_large_dimension_limits(native, O):
     (1, (-3, 3), 1.0, 25, 30),        # one boson: d = 2
     (3, (-3, 3, 3), 0.0, 25, 30),     # dense path without hopping
     (40, (-3, 3), 1.0, 25, 30),       # large-d split path, tridiagonal
+    (40, (-3, 3), 1.0, 25, 1),        # large-d, DMMA evolution: a single sample (chunks of 8 samples, 7 padded)
+    (36, (-3, 3), 1.0, 25, 13),       # large-d, DMMA evolution: ragged last chunk
+    (5, (-3, 3, 3), 1.0, 25, 67),     # dense large-d (d = 21 -> 32), nine chunks, the last one ragged
+    (7, (-3, 3, 3), 1.5, 20, 8),      # dense large-d (d = 36 -> 48), exactly one chunk
 ])
 def test_unusual_constants(native, O, N, omegas, coupling, max_t, timesteps):
     c = make_const(N, omegas, coupling=coupling, max_t=max_t, timesteps=timesteps)
