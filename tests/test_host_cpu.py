@@ -144,3 +144,19 @@ def test_global_argmin_gloo_world2(tmp_path, built_lib):
         out, err = p.communicate(timeout=180)
         assert p.returncode == 0, err[-2000:]
         assert "ok" in out
+
+
+def test_bench_cpu_baseline_sample_is_bounded():
+    """bench.py's CPU baseline (the oracle over a process pool) must stay a bounded sample for every workload: at d = 101 an
+    unpinned BLAS oversubscribed the cores and one `--workload dimer100` run spent 13 minutes in it."""
+    import time
+    sys.path.insert(0, ROOT)
+    import bench
+    w = bench.WORKLOADS["dimer100"]
+    const = bench.make_const(w)
+    pts = bench.make_points(w)[:4096]
+    t0 = time.perf_counter()
+    rate, n, dt = bench.cpu_rate(const, pts, cores=2, seconds_target=2.0)
+    wall = time.perf_counter() - t0
+    assert 16 <= n <= len(pts) and rate > 0
+    assert dt < 20.0 and wall < 40.0, (n, dt, wall)

@@ -25,4 +25,5 @@ names = ["hh 0 build H row", "hh 1 reduction", "hh 2 Q accumulation", "hh 3 stor
 print(f"N={N} f={len(om)} d={prob.dim} B={B} step {e0.elapsed_time(e1):.3f} ms ; CTA-cycles per point:")
 for i, n in enumerate(names):
     print(f"  {n:26s} {out[i]/B:10.1f}")
-print(f"  per point: active rounds {out[10]/B:.1f}  own-window planes {out[11]/B:.0f}  batch-window planes {out[12]/B:.0f}  trip steps {out[13]/B:.0f}  trips {out[14]/B:.1f}")
+if any(out[i] for i in range(10, 15)):       # replay statistics (only in builds that count them)
+    print(f"  per point: active rounds {out[10]/B:.1f}  own-window planes {out[11]/B:.0f}  batch-window planes {out[12]/B:.0f}  trip steps {out[13]/B:.0f}  trips {out[14]/B:.1f}")
