@@ -10,8 +10,10 @@
 //                             Q = H_0 H_1 ... in the same registers; writes (diag, off) and Q (column-major).
 //   replay_reg_kernel<D, NW>  V <- I (or Q); replays the plane rotations recorded by ql_scalar_big_kernel on the
 //                             register rows (statically indexed, plane groups skipped with warp-uniform branches),
-//                             then psi(t) = V (c . exp(-i e t)) (HamiltonianLoss.py:204-215), loss (:227-231) and the
-//                             analytic gradient through the symmetrised Daleckii-Krein kernel (replaces Optimizer.py:85-91).
+//                             then psi(t) = V (c . exp(-i e t)) (HamiltonianLoss.py:204-215) as FP64 tensor-core products
+//                             (mma.sync m8n8k4: V parked in shared memory is the A operand, the phase table of 8 time
+//                             samples the B operand), loss (:227-231) and the analytic gradient through the symmetrised
+//                             Daleckii-Krein kernel (replaces Optimizer.py:85-91).
 //
 // D is the compile-time padded dimension (register arrays must be statically indexed), NW = ceil(D / 32) warps.
 #include <cstdlib>
