@@ -262,7 +262,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="dimer20", choices=sorted(WORKLOADS))
-    ap.add_argument("--path", default="auto", choices=["auto", "generic", "split"])
+    ap.add_argument("--path", default="auto", choices=["auto", "generic", "split", "direct"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the trimer N=10 side measurement of the default run")
     ap.add_argument("--points", type=int, default=0, help="override the number of points per GPU (random workloads: any size; grid: truncation)")
@@ -294,8 +294,8 @@ def main():
 
     prob = _native.Problem.from_const(const, device=local)
     if args.path != "auto":
-        prob.set_path({"generic": _native.QTET_PATH_GENERIC, "split": _native.QTET_PATH_SPLIT}[args.path])
-    path_name = {1: "generic", 2: "split"}[prob.get_path()]
+        prob.set_path({"generic": _native.QTET_PATH_GENERIC, "split": _native.QTET_PATH_SPLIT, "direct": _native.QTET_PATH_DIRECT}[args.path])
+    path_name = _native.PATH_NAMES[prob.get_path()]
     if args.points and w["kind"] == "random" and args.points != w["B"]:
         # BASELINE's full sizes (config 3: 2^18 dimer N=100 points, config 4: 2^20 trimer N=10 points) are reached this way
         w = dict(w, B=args.points, label=w["label"].replace("2^14", str(args.points)).replace("2^16", str(args.points)))

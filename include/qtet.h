@@ -38,10 +38,12 @@ extern "C" {
 typedef struct qtet_problem qtet_problem;
 
 /* Kernel family selection for qtet_set_path (diagnostics / parity tests). */
-#define QTET_PATH_AUTO    0    /* fast split path when eligible, fused generic otherwise */
+#define QTET_PATH_AUTO    0    /* direct path when eligible, else the split paths, else fused generic */
 #define QTET_PATH_GENERIC 1    /* fused CTA-per-point kernel, any system */
 #define QTET_PATH_SPLIT   2    /* thread-per-point scalar QL + rotation replay (register path for tridiagonal d<=32,
                                   shared-memory replay for d<=128 incl. dense H after Householder) */
+#define QTET_PATH_DIRECT  3    /* tridiagonal d<=32 with non-zero hopping: eigenvalues by scalar QL, eigenvectors by
+                                  two-sided three-term recurrences (twisted factorisation), no rotation stream */
 
 /*
  * Build the chi-independent part of the problem once: Fock basis in the reference's order
@@ -66,7 +68,7 @@ int qtet_hamiltonian_host(qtet_problem* p, const double* chis_host, double* H_ho
 
 /* Choose the kernel family (QTET_PATH_*); QTET_EUNSUPPORTED if the problem is not eligible. */
 int qtet_set_path(qtet_problem* p, int path);
-/* Which family the next call will use (QTET_PATH_GENERIC or QTET_PATH_SPLIT). */
+/* Which family the next call will use (QTET_PATH_GENERIC, QTET_PATH_SPLIT or QTET_PATH_DIRECT). */
 int qtet_get_path(const qtet_problem* p);
 
 /*

@@ -45,8 +45,17 @@ int ensure_scratch(qtet_problem* p, size_t bytes) {
     return QTET_OK;
 }
 
+static int auto_path(const ProblemView& v) {
+    if (direct_eligible(v)) return QTET_PATH_DIRECT;
+    return (split_eligible(v) || big_eligible(v)) ? QTET_PATH_SPLIT : QTET_PATH_GENERIC;
+}
+
 int loss_grad_dispatch(qtet_problem* p, const double* chis, int64_t B, int site, double* loss,
-                       double* grad, int32_t* tstar, double* trace, cudaStream_t st, const ChunkHook* hook) {
+                       double* grad, int32_t* tstar, double* trace, cudaStream_t st, const ChunkHook* hook,
+                       const int* n_dev) {
+    if (p->path == QTET_PATH_DIRECT)
+        return launch_direct(p->view, &p->direct_ws, chis, B, n_dev, site, loss, grad, tstar, trace, st, p->prof.on ? &p->prof : nullptr, hook);
+    if (n_dev) { set_error("a device-side batch size is only supported on the direct path"); return QTET_EINVAL; }
     if (p->path == QTET_PATH_SPLIT && !split_eligible(p->view))
         return launch_big(p->view, &p->big_ws, chis, B, site, loss, grad, tstar, trace, st, p->prof.on ? &p->prof : nullptr);
     if (p->path == QTET_PATH_SPLIT)
@@ -114,6 +123,8 @@ int qtet_problem_create(int max_N, int sites, const double* omegas, double coupl
         }
     }
     p->tridiag = bandwidth <= 1;
+    bool offd_nonzero = p->tridiag && d >= 2;
+    for (int m = 0; m + 1 < d && offd_nonzero; ++m) offd_nonzero = dense[(size_t)(m + 1) * d + m] != 0.0;
     // time grid = numpy.linspace(0, max_t, T): k*step, last sample exactly max_t
     p->tgrid.resize(timesteps);
     if (timesteps == 1) p->tgrid[0] = 0.0;
@@ -149,10 +160,10 @@ int qtet_problem_create(int max_N, int sites, const double* omegas, double coupl
     e = cudaMemcpy(p->dev_blob, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(p->dev_blob); delete p; return cuda_fail(e, "cudaMemcpy(constants)"); }
     ProblemView& v = p->view;
-    v.N = max_N; v.f = sites; v.d = d; v.T = timesteps; v.tridiag = p->tridiag ? 1 : 0; v.max_t = max_t;
+    v.N = max_N; v.f = sites; v.d = d; v.T = timesteps; v.tridiag = p->tridiag ? 1 : 0; v.offd_nonzero = offd_nonzero ? 1 : 0; v.max_t = max_t;
     v.lin = p->dev_blob + o_lin; v.quad = p->dev_blob + o_quad; v.occ = p->dev_blob + o_occ;
     v.offd = p->dev_blob + o_off; v.tgrid = p->dev_blob + o_t; v.omegas = p->dev_blob + o_om;
-    p->path = (split_eligible(v) || big_eligible(v)) ? QTET_PATH_SPLIT : QTET_PATH_GENERIC;
+    p->path = auto_path(v);
     *out = p;
     return QTET_OK;
 }
@@ -170,6 +181,7 @@ void qtet_problem_destroy(qtet_problem* p) {
         if (p->ev_run[i]) cudaEventDestroy(p->ev_run[i]);
     }
     split_workspace_free(p->split_ws);
+    direct_workspace_free(p->direct_ws);
     big_workspace_free(p->big_ws);
     p->prof.clear();
     delete p;
@@ -191,7 +203,12 @@ int qtet_problem_time_grid(const qtet_problem* p, double* t_host) {
 
 int qtet_set_path(qtet_problem* p, int path) {
     if (!p) { set_error("null handle"); return QTET_EINVAL; }
-    if (path == QTET_PATH_AUTO) { p->path = (split_eligible(p->view) || big_eligible(p->view)) ? QTET_PATH_SPLIT : QTET_PATH_GENERIC; return QTET_OK; }
+    if (path == QTET_PATH_AUTO) { p->path = auto_path(p->view); return QTET_OK; }
+    if (path == QTET_PATH_DIRECT) {
+        if (!direct_eligible(p->view)) { set_error("direct path needs a tridiagonal H with non-zero hopping and dim <= 32"); return QTET_EUNSUPPORTED; }
+        p->path = path;
+        return QTET_OK;
+    }
     if (path == QTET_PATH_GENERIC) { p->path = path; return QTET_OK; }
     if (path == QTET_PATH_SPLIT) {
         if (!split_eligible(p->view) && !big_eligible(p->view)) { set_error("split path needs dim <= 128"); return QTET_EUNSUPPORTED; }
@@ -284,7 +301,7 @@ int qtet_loss_grad_host(qtet_problem* p, const double* chis_host, int64_t B, int
         if (c.tstar_host) QTET_CUDA(cudaMemcpyAsync(c.tstar_host + lo, c.dts + lo, (size_t)n * 4, cudaMemcpyDeviceToHost, c.p->s_out));
         return QTET_OK;
     };
-    const bool chunked = (p->path == QTET_PATH_SPLIT && split_eligible(p->view));
+    const bool chunked = (p->path == QTET_PATH_DIRECT) || (p->path == QTET_PATH_SPLIT && split_eligible(p->view));
     if (chunked) {
         ChunkHook hook;
         hook.ctx = &cx; hook.before = copy_in; hook.after = copy_out;

@@ -13,6 +13,7 @@ namespace qtet {
 struct ProblemView {
     int N, f, d, T;
     int tridiag;          // 1: H is tridiagonal in the reference's basis order (dimer)
+    int offd_nonzero;     // tridiag only: every off-diagonal element is non-zero (the direct recurrences divide by them)
     double max_t;
     const double* lin;    // [d]     sum_k omega_k n_k(m)                 HamiltonianLoss.py:132-133
     const double* quad;   // [d, f]  n_k(m)^2 / 2 = dH_mm/dchi_k          HamiltonianLoss.py:134
@@ -84,6 +85,15 @@ int launch_split(const ProblemView& pv, SplitWorkspace** ws, const double* chis,
                  const ChunkHook* hook = nullptr);
 void split_workspace_free(SplitWorkspace* ws);
 
+struct DirectWorkspace;  // eigenvalues by QL + eigenvectors by two-sided recurrences, tridiagonal d <= 32 (qtet_direct.cu)
+bool direct_eligible(const ProblemView& pv);
+// n_dev (optional, device pointer): process min(B, *n_dev) points -- the optimiser's compacted live list, no host round trip
+int launch_direct(const ProblemView& pv, DirectWorkspace** ws, const double* chis, int64_t B, const int* n_dev, int site,
+                  double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st, Profiler* prof = nullptr,
+                  const ChunkHook* hook = nullptr);
+int direct_reserve(const ProblemView& pv, DirectWorkspace** ws, int64_t B);
+void direct_workspace_free(DirectWorkspace* ws);
+
 struct BigWorkspace;     // large-d split path (qtet_big.cu)
 bool big_eligible(const ProblemView& pv);
 int launch_big(const ProblemView& pv, BigWorkspace** ws, const double* chis, int64_t B, int site, double* loss,
@@ -105,6 +115,7 @@ struct qtet_problem {
     double* dev_blob = nullptr;             // one allocation holding every constant array
     qtet::ProblemView view{};
     qtet::SplitWorkspace* split_ws = nullptr;
+    qtet::DirectWorkspace* direct_ws = nullptr;
     qtet::BigWorkspace* big_ws = nullptr;
     qtet::Profiler prof;
     // scratch for *_host convenience calls and the optimiser
@@ -119,7 +130,8 @@ struct qtet_problem {
 namespace qtet {
 int ensure_scratch(qtet_problem* p, size_t bytes);
 int loss_grad_dispatch(qtet_problem* p, const double* chis, int64_t B, int site, double* loss,
-                       double* grad, int32_t* tstar, double* trace, cudaStream_t st, const ChunkHook* hook = nullptr);
+                       double* grad, int32_t* tstar, double* trace, cudaStream_t st, const ChunkHook* hook = nullptr,
+                       const int* n_dev = nullptr);
 }
 
 // ---- device helpers ---------------------------------------------------------------------

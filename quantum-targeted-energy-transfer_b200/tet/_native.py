@@ -14,7 +14,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("QTET_B200_LIB", os.path.join(_HERE, "..", "lib", "libqtet_b200.so"))
 
-QTET_PATH_AUTO, QTET_PATH_GENERIC, QTET_PATH_SPLIT = 0, 1, 2
+QTET_PATH_AUTO, QTET_PATH_GENERIC, QTET_PATH_SPLIT, QTET_PATH_DIRECT = 0, 1, 2, 3
+PATH_NAMES = {1: "generic", 2: "split", 3: "direct"}
 
 
 class QtetError(RuntimeError):

@@ -286,15 +286,16 @@ def test_split_and_generic_paths_agree(native):
     rng = np.random.default_rng(11)
     X = rng.uniform(-10, 10, (4096, 2))
     p = native.Problem.from_const(c)
-    if p.get_path() != native.QTET_PATH_SPLIT:
-        pytest.skip("split path not built")
-    a = [t.cpu().numpy() for t in p.loss_grad(X, 1)]
+    assert p.get_path() == native.QTET_PATH_DIRECT          # what AUTO picks for a dimer with hopping
     p.set_path(native.QTET_PATH_GENERIC)
     b = [t.cpu().numpy() for t in p.loss_grad(X, 1)]
-    assert np.abs(a[0] - b[0]).max() < 2e-9
-    same = a[2] == b[2]
-    assert same.mean() > 0.999
-    assert (np.abs(a[1] - b[1]) / np.maximum(1, np.abs(b[1]).max(axis=1, keepdims=True)))[same].max() < 1e-7
+    for path in (native.QTET_PATH_DIRECT, native.QTET_PATH_SPLIT):
+        p.set_path(path)
+        a = [t.cpu().numpy() for t in p.loss_grad(X, 1)]
+        assert np.abs(a[0] - b[0]).max() < 2e-9
+        same = a[2] == b[2]
+        assert same.mean() > 0.999
+        assert (np.abs(a[1] - b[1]) / np.maximum(1, np.abs(b[1]).max(axis=1, keepdims=True)))[same].max() < 1e-7
     p.close()
 
 
@@ -312,7 +313,7 @@ from oracle import qtet_oracle as O
 c = {{"max_N": 20, "sites": 2, "max_t": 25, "omegas": [-3, 3], "chis": [0, 0], "coupling": 1, "timesteps": 30}}
 X = np.random.default_rng(9).uniform(-10, 10, (333, 2))
 p = _native.Problem.from_const(c)
-assert p.get_path() == _native.QTET_PATH_SPLIT
+p.set_path(_native.QTET_PATH_SPLIT)
 L, g, k = p.loss_grad_host(X, 1)
 Lr, gr, kr = O.loss_grad_batch(c, X, 1)
 assert np.abs(L - Lr).max() < 2e-9 and (k == kr).all() and np.abs(g - gr).max() < 1e-7 * max(1, np.abs(gr).max())
