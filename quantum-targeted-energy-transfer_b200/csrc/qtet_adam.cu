@@ -6,6 +6,7 @@
 // ">2 sub-tol moves" stop.  Guesses that stopped are compacted away so that the loss+grad kernels only
 // ever see live guesses (ragged convergence).
 #include <cmath>
+#include <cstdlib>
 #include <limits>
 
 #include "qtet_common.cuh"
@@ -16,7 +17,9 @@ namespace {
 
 struct AdamArgs {
     int f;
-    long long n_active;
+    long long n_active;       // upper bound known to the host ...
+    const int* n_dev;         // ... and, when non-null, the exact count on the device
+    int* cnt_next;            // counter the NEXT epoch's compaction accumulates into (zeroed here)
     const int* active;        // [n_active] guess ids
     const double* xc;         // [n_active, f] compacted variables the loss/grad was evaluated at
     const double* loss;       // [n_active]
@@ -42,7 +45,9 @@ struct AdamArgs {
 // Optimizer.py:146-224, one epoch for every live guess.
 __global__ void adam_step_kernel(AdamArgs a) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= a.n_active) return;
+    if (i == 0 && a.cnt_next) *a.cnt_next = 0;
+    const long long n = a.n_dev ? (long long)*a.n_dev : a.n_active;
+    if (i >= n) return;
     const int b = a.active[i];
     const int f = a.f;
     const double L = a.loss[i];
@@ -115,6 +120,28 @@ __global__ void gather_kernel(const int* active, long long n, int f, const doubl
     const long long r = i / f;
     const int k = (int)(i - r * f);
     xc[i] = x[(long long)active[r] * f + k];
+}
+
+// Compaction and gather in one launch over the PREVIOUS live list (a guess can only leave it): new live list,
+// its variables, and its length -- all on the device, the host never needs the count to size a launch.
+//   prev == nullptr: first epoch, every guess 0 .. n_prev-1 is a candidate.
+__global__ void compact_gather_kernel(const int* alive, const int* prev, long long n_prev_host, const int* n_prev_dev,
+                                      int f, const double* x, int* active, double* xc, int* n_active) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long n_prev = n_prev_dev ? (long long)*n_prev_dev : n_prev_host;
+    int b = -1;
+    if (i < n_prev) b = prev ? prev[i] : (int)i;
+    const bool live = (b >= 0) && alive[b];
+    const unsigned ballot = __ballot_sync(0xffffffffu, live);
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0 && ballot) base = atomicAdd(n_active, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (live) {
+        const int slot = base + __popc(ballot & ((1u << lane) - 1u));
+        active[slot] = b;
+        for (int k = 0; k < f; ++k) xc[(long long)slot * f + k] = x[(long long)b * f + k];
+    }
 }
 
 __global__ void adam_init_kernel(long long B, int f, double N, double lr, double* m, double* v, double* vhat,
@@ -207,7 +234,7 @@ extern "C" int qtet_adam_run(qtet_problem* p, double* chis_dev, int64_t B, int t
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     const size_t o_m = take(Bf * 8), o_v = take(Bf * 8), o_vh = take(Bf * 8), o_lr = take(B * 8), o_last = take(B * 8),
                  o_xc = take(Bf * 8), o_loss = take(B * 8), o_grad = take(Bf * 8), o_err = take(Bf * 4),
-                 o_alive = take(B * 4), o_active = take(B * 4), o_ep = take(B * 4), o_cnt = take(256);
+                 o_alive = take(B * 4), o_active = take(2 * (size_t)B * 4), o_ep = take(B * 4), o_cnt = take(256);
     int rc = ensure_scratch(p, off);
     if (rc) return rc;
     char* base = (char*)p->scratch;
@@ -216,8 +243,16 @@ extern "C" int qtet_adam_run(qtet_problem* p, double* chis_dev, int64_t B, int t
            *gradc = (double*)(base + o_grad);
     int *err = (int*)(base + o_err), *alive = (int*)(base + o_alive), *active = (int*)(base + o_active),
         *ep = (int*)(base + o_ep), *cnt = (int*)(base + o_cnt);
-    int* h_cnt = nullptr;
-    QTET_CUDA(cudaMallocHost(&h_cnt, sizeof(int)));
+    // pinned host words for the live counts + their events: allocated once per handle
+    constexpr int kRing = qtet_problem::kPollRing;
+    if (!p->h_poll) {
+        QTET_CUDA(cudaMallocHost(&p->h_poll, kRing * sizeof(int)));
+        QTET_CUDA(cudaStreamCreateWithFlags(&p->s_poll, cudaStreamNonBlocking));
+        for (int i = 0; i < kRing; ++i) {
+            QTET_CUDA(cudaEventCreateWithFlags(&p->ev_cnt[i], cudaEventDisableTiming));
+            QTET_CUDA(cudaEventCreateWithFlags(&p->ev_poll[i], cudaEventDisableTiming));
+        }
+    }
 
     const int TPB = 256;
     const unsigned gB = (unsigned)((B + TPB - 1) / TPB);
@@ -233,42 +268,96 @@ extern "C" int qtet_adam_run(qtet_problem* p, double* chis_dev, int64_t B, int t
         fill_nan_kernel<<<(unsigned)((n + TPB - 1) / TPB), TPB, 0, st>>>(var_hist_dev, n);
         count_launch();
     }
-    int epoch = 0;
-    long long n_active = B;
-    for (; epoch < iterations; ++epoch) {
-        // live list (compaction) -- sync point: the host needs the count to size the launches
-        cudaMemsetAsync(cnt, 0, sizeof(int), st);
-        compact_kernel<<<gB, TPB, 0, st>>>(alive, (long long)B, active, cnt);
-        count_launch();
-        cudaMemcpyAsync(h_cnt, cnt, sizeof(int), cudaMemcpyDeviceToHost, st);
-        cudaError_t e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) { cudaFreeHost(h_cnt); return cuda_fail(e, "adam: sync"); }
-        n_active = *h_cnt;
-        if (n_active == 0) break;
-        const long long nf = n_active * f;
-        gather_kernel<<<(unsigned)((nf + TPB - 1) / TPB), TPB, 0, st>>>(active, n_active, f, chis_dev, xc);
-        count_launch();
-        rc = loss_grad_dispatch(p, xc, n_active, target_site, lossc, gradc, nullptr, nullptr, st);
-        if (rc) { cudaFreeHost(h_cnt); return rc; }
-        AdamArgs a;
-        a.f = f; a.n_active = n_active; a.active = active; a.xc = xc; a.loss = lossc; a.grad = gradc;
-        a.x = chis_dev; a.m = m; a.v = v; a.vhat = vh; a.lr = lrv; a.last_loss = last; a.min_loss = best_loss_dev;
-        a.best_vars = best_vars_dev; a.err_count = err; a.alive = alive; a.epochs = ep; a.train_mask = mask;
-        a.beta_1 = beta_1; a.beta_2 = beta_2; a.epsilon = epsilon; a.tol = tol;
-        const int t = epoch + 1;
-        a.s2 = std::sqrt(1.0 - std::pow(beta_2, (double)t));
-        a.s1 = 1.0 - std::pow(beta_1, (double)t);
-        a.amsgrad = amsgrad; a.epoch = epoch; a.B = B; a.loss_hist = loss_hist_dev; a.var_hist = var_hist_dev;
-        adam_step_kernel<<<(unsigned)((n_active + TPB - 1) / TPB), TPB, 0, st>>>(a);
-        count_launch();
+    AdamArgs a;
+    a.f = f; a.xc = xc; a.loss = lossc; a.grad = gradc;
+    a.x = chis_dev; a.m = m; a.v = v; a.vhat = vh; a.lr = lrv; a.last_loss = last; a.min_loss = best_loss_dev;
+    a.best_vars = best_vars_dev; a.err_count = err; a.alive = alive; a.epochs = ep; a.train_mask = mask;
+    a.beta_1 = beta_1; a.beta_2 = beta_2; a.epsilon = epsilon; a.tol = tol;
+    a.amsgrad = amsgrad; a.B = B; a.loss_hist = loss_hist_dev; a.var_hist = var_hist_dev;
+
+    // The loss+grad kernels of the direct path read the number of live guesses from device memory, so the epoch loop
+    // never waits for the GPU: the host only keeps an UPPER BOUND of the live count (it can only fall) to size the grids,
+    // refreshed from a pinned word that trails the device by kLag epochs, and stops once that word reads zero.
+    const bool devcount = (p->path == QTET_PATH_DIRECT) && B <= (1LL << 22) && !std::getenv("QTET_ADAM_SYNC");
+    int epoch = 0, executed = -1;
+    if (devcount) {
+        constexpr int kLag = 4;
+        static_assert(kLag < kRing, "poll ring too small");
+        QTET_CUDA(cudaMemsetAsync(cnt, 0, 2 * sizeof(int), st));
+        long long n_bound = B;
+        for (; epoch < iterations; ++epoch) {
+            if (epoch >= kLag) {                        // live count that ENTERED epoch - kLag
+                const int slot = (epoch - kLag) % kRing;
+                cudaError_t e = cudaEventSynchronize(p->ev_poll[slot]);
+                if (e != cudaSuccess) return cuda_fail(e, "adam: poll");
+                const long long nlive = p->h_poll[slot];
+                if (nlive == 0) { executed = epoch - kLag; break; }
+                if (nlive < n_bound) n_bound = nlive;
+            }
+            const int cur = epoch & 1;
+            int* act_cur = active + (size_t)cur * B;
+            const int* act_prev = epoch ? active + (size_t)(1 - cur) * B : nullptr;
+            compact_gather_kernel<<<(unsigned)((n_bound + TPB - 1) / TPB), TPB, 0, st>>>(
+                alive, act_prev, n_bound, epoch ? cnt + (1 - cur) : nullptr, f, chis_dev, act_cur, xc, cnt + cur);
+            count_launch();
+            // the count leaves on a side stream so that the D2H copy never sits between two kernels of the epoch
+            const int slot = epoch % kRing;
+            QTET_CUDA(cudaEventRecord(p->ev_cnt[slot], st));
+            QTET_CUDA(cudaStreamWaitEvent(p->s_poll, p->ev_cnt[slot], 0));
+            QTET_CUDA(cudaMemcpyAsync(p->h_poll + slot, cnt + cur, sizeof(int), cudaMemcpyDeviceToHost, p->s_poll));
+            QTET_CUDA(cudaEventRecord(p->ev_poll[slot], p->s_poll));
+            rc = loss_grad_dispatch(p, xc, n_bound, target_site, lossc, gradc, nullptr, nullptr, st, nullptr, cnt + cur);
+            if (rc) return rc;
+            a.n_active = n_bound; a.n_dev = cnt + cur; a.cnt_next = cnt + (1 - cur); a.active = act_cur;
+            const int t = epoch + 1;
+            a.s2 = std::sqrt(1.0 - std::pow(beta_2, (double)t));
+            a.s1 = 1.0 - std::pow(beta_1, (double)t);
+            a.epoch = epoch;
+            // cnt[1 - cur] is zeroed by this kernel: the copy of the previous epoch's count must have left it
+            if (epoch) QTET_CUDA(cudaStreamWaitEvent(st, p->ev_poll[(epoch - 1) % kRing], 0));
+            adam_step_kernel<<<(unsigned)((n_bound + TPB - 1) / TPB), TPB, 0, st>>>(a);
+            count_launch();
+        }
+        if (executed < 0) {                             // ran out of iterations: settle the polls still in flight
+            cudaError_t e = cudaStreamSynchronize(p->s_poll);
+            if (e != cudaSuccess) return cuda_fail(e, "adam: poll sync");
+            executed = epoch;
+            for (int e2 = (epoch > kLag ? epoch - kLag : 0); e2 < epoch; ++e2)
+                if (p->h_poll[e2 % kRing] == 0) { executed = e2; break; }
+        }
+    } else {
+        long long n_active = B;
+        for (; epoch < iterations; ++epoch) {
+            // live list (compaction) -- sync point: the host needs the count to size the launches
+            cudaMemsetAsync(cnt, 0, sizeof(int), st);
+            compact_kernel<<<gB, TPB, 0, st>>>(alive, (long long)B, active, cnt);
+            count_launch();
+            cudaMemcpyAsync(p->h_poll, cnt, sizeof(int), cudaMemcpyDeviceToHost, st);
+            cudaError_t e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) return cuda_fail(e, "adam: sync");
+            n_active = p->h_poll[0];
+            if (n_active == 0) break;
+            const long long nf = n_active * f;
+            gather_kernel<<<(unsigned)((nf + TPB - 1) / TPB), TPB, 0, st>>>(active, n_active, f, chis_dev, xc);
+            count_launch();
+            rc = loss_grad_dispatch(p, xc, n_active, target_site, lossc, gradc, nullptr, nullptr, st);
+            if (rc) return rc;
+            a.n_active = n_active; a.n_dev = nullptr; a.cnt_next = nullptr; a.active = active;
+            const int t = epoch + 1;
+            a.s2 = std::sqrt(1.0 - std::pow(beta_2, (double)t));
+            a.s1 = 1.0 - std::pow(beta_1, (double)t);
+            a.epoch = epoch;
+            adam_step_kernel<<<(unsigned)((n_active + TPB - 1) / TPB), TPB, 0, st>>>(a);
+            count_launch();
+        }
+        executed = epoch;
     }
     if (epochs_dev) cudaMemcpyAsync(epochs_dev, ep, (size_t)B * 4, cudaMemcpyDeviceToDevice, st);
     cudaError_t e = cudaStreamSynchronize(st);
-    cudaFreeHost(h_cnt);
     if (e != cudaSuccess) return cuda_fail(e, "adam: final sync");
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "adam: kernel");
-    return epoch;
+    return executed;
 }
 
 extern "C" int qtet_fp64_peak(int device, double seconds_budget, double* tflops_out) {

@@ -176,6 +176,12 @@ void qtet_problem_destroy(qtet_problem* p) {
     if (p->s_in) cudaStreamDestroy(p->s_in);
     if (p->s_run) cudaStreamDestroy(p->s_run);
     if (p->s_out) cudaStreamDestroy(p->s_out);
+    if (p->s_poll) cudaStreamDestroy(p->s_poll);
+    if (p->h_poll) cudaFreeHost(p->h_poll);
+    for (int i = 0; i < qtet_problem::kPollRing; ++i) {
+        if (p->ev_cnt[i]) cudaEventDestroy(p->ev_cnt[i]);
+        if (p->ev_poll[i]) cudaEventDestroy(p->ev_poll[i]);
+    }
     for (int i = 0; i < qtet_problem::kMaxSlices; ++i) {
         if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);
         if (p->ev_run[i]) cudaEventDestroy(p->ev_run[i]);

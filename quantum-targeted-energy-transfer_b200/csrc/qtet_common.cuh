@@ -91,7 +91,7 @@ bool direct_eligible(const ProblemView& pv);
 int launch_direct(const ProblemView& pv, DirectWorkspace** ws, const double* chis, int64_t B, const int* n_dev, int site,
                   double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st, Profiler* prof = nullptr,
                   const ChunkHook* hook = nullptr);
-int direct_reserve(const ProblemView& pv, DirectWorkspace** ws, int64_t B);
+int direct_reserve(const ProblemView& pv, DirectWorkspace** ws, int64_t B, bool single_chunk = false);
 void direct_workspace_free(DirectWorkspace* ws);
 
 struct BigWorkspace;     // large-d split path (qtet_big.cu)
@@ -125,6 +125,11 @@ struct qtet_problem {
     static constexpr int kMaxSlices = 64;
     cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[kMaxSlices] = {}, ev_run[kMaxSlices] = {};
+    // qtet_adam_run: pinned words the live counts are copied to (one per epoch, ring), their events, the copy stream
+    static constexpr int kPollRing = 16;
+    int* h_poll = nullptr;
+    cudaStream_t s_poll = nullptr;
+    cudaEvent_t ev_cnt[kPollRing] = {}, ev_poll[kPollRing] = {};
 };
 
 namespace qtet {

@@ -35,6 +35,7 @@ constexpr int kWarpsE = 4;                              // warps per CTA, eigenv
 constexpr double kGapGS = 2.44140625e-4;                // 2^-12: re-orthogonalise neighbours closer than this (x ||T||)
 constexpr double kGapFB = 5.820766091346741e-11;        // 2^-34: numerically degenerate -> generic kernel
 constexpr int kMaxF = 8;
+constexpr double kCsig = 1e-19;                         // eigenvectors with |c_i| below this carry no weight in psi(t)
 
 // Shifted diagonal of H.  The two kernels must see bit-identical values, hence explicit fma / no contraction freedom:
 // a_m = lin_m + sum_k chi_k quad_mk  (HamiltonianLoss.py:131-134 with lin = sum_k omega_k n_k, quad = n_k^2 / 2).
@@ -60,6 +61,7 @@ __global__ void __launch_bounds__(kWarpsE * 32) eig_scalar_kernel(SplitArgs a) {
     const long long n = effective_n(a);
     const long long nbatch = (n + 31) / 32;
     const unsigned below_top = lowmask(d - 1);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.fb_count = 0;    // K_D of this chunk (stream-ordered after us) appends to the list
     for (long long batch = (long long)blockIdx.x * kWarpsE + warp; batch < nbatch; batch += (long long)gridDim.x * kWarpsE) {
         const long long p = batch * 32 + lane;
         const bool valid = p < n;
@@ -383,25 +385,54 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) direct_kernel(SplitArgs a) {
                 a.fb_list[slot] = (int)p;
             }
         }
+        // ---- order the eigen-indices by |c_i| = |V[0][i]| descending (ties by index): rank of my own indices against all
+        double* evs = abuf + g * D;                                   // [D] eigenvalues in the new order (ap is dead)
+        int* perm = reinterpret_cast<int*>(abuf + PPW * D) + g * D;   // [D] new position -> eigen-index
+        int nsig = 0;
+        {
+            double cabs[RZ];
+            int rank[RZ];
+#pragma unroll
+            for (int t = 0; t < RZ; ++t) {
+                const int i = q + t * G;
+                cabs[t] = (i < D) ? fabs(vp[i] * rnbuf[g * D + i]) : 0.0;
+                rank[t] = 0;
+                if (i < D && cabs[t] > kCsig) ++nsig;
+            }
+#pragma unroll 1
+            for (int j = 0; j < D; ++j) {
+                const double cj = fabs(vp[j] * rnbuf[g * D + j]);
+#pragma unroll
+                for (int t = 0; t < RZ; ++t) {
+                    const int i = q + t * G;
+                    if (cj > cabs[t] || (cj == cabs[t] && j < i)) ++rank[t];
+                }
+            }
+            __syncwarp();                                             // everyone is done with ap (aliases evs)
+#pragma unroll
+            for (int t = 0; t < RZ; ++t) {
+                const int i = q + t * G;
+                if (i < D) { evs[rank[t]] = lam[t]; perm[rank[t]] = i; }
+            }
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) nsig += __shfl_xor_sync(0xffffffffu, nsig, o);
+        }
+        int ncol = __reduce_max_sync(0xffffffffu, nsig);
+        if (ncol < 1) ncol = 1;
+        __syncwarp();
         double v[R][D];
 #pragma unroll
-        for (int k = 0; k < R; ++k) {
-            const int row = q * R + k;
-            if (row < D) {
-                const double* rp = vp + row * LDV;
+        for (int i = 0; i < D; ++i) {
+            const int src = perm[i];
+            const double rn = rnbuf[g * D + src];
 #pragma unroll
-                for (int i = 0; i + 1 < D; i += 2) {
-                    const double2 x = *reinterpret_cast<const double2*>(rp + i);
-                    v[k][i] = x.x * rnbuf[g * D + i]; v[k][i + 1] = x.y * rnbuf[g * D + i + 1];
-                }
-                if (D & 1) v[k][D - 1] = rp[D - 1] * rnbuf[g * D + D - 1];
-            } else {
-#pragma unroll
-                for (int i = 0; i < D; ++i) v[k][i] = 0.0;
+            for (int k = 0; k < R; ++k) {
+                const int row = q * R + k;
+                v[k][i] = (row < D) ? vp[row * LDV + src] * rn : 0.0;
             }
         }
         PHASE_MARK(1);
-        evolve_and_grad<D, G>(a, v, wsite, lv, part, sbuf, zbuf, cbuf, p, valid, g, q, lane, dt, _t0);
+        evolve_and_grad<D, G, true>(a, v, wsite, lv, part, sbuf, zbuf, cbuf, p, valid, g, q, lane, dt, _t0, evs, ncol, nsig);
     }
 }
 
@@ -519,11 +550,12 @@ static int direct_workspace_init(const ProblemView& pv, DirectWorkspace** wsp) {
 }
 
 // chunk size (points) the path would use for a batch of B points
-static long long direct_chunk(long long B) {
+static long long direct_chunk(long long B, bool single) {
+    const long long all = (B + 31) / 32 * 32;
+    if (single) return all;                                  // device-side batch size: one chunk (B <= 2^22 checked by the caller)
     long long chunk = ((B + 3) / 4 + 31) / 32 * 32;          // four chunks per call: K_E(c+1) overlaps K_D(c)
     if (chunk < 65536) chunk = 65536;
     if (chunk > (1LL << 22)) chunk = 1LL << 22;
-    const long long all = (B + 31) / 32 * 32;
     if (chunk > all) chunk = all;
     return chunk;
 }
@@ -535,11 +567,11 @@ static size_t direct_buf_bytes(long long chunk, int d) {
 }
 
 // Make the workspace large enough for batches of up to B points, so that later calls neither allocate nor synchronise.
-int direct_reserve(const ProblemView& pv, DirectWorkspace** wsp, int64_t B) {
+int direct_reserve(const ProblemView& pv, DirectWorkspace** wsp, int64_t B, bool single) {
     int rc = direct_workspace_init(pv, wsp);
     if (rc) return rc;
     DirectWorkspace* ws = *wsp;
-    const size_t total = 2 * direct_buf_bytes(direct_chunk(B), pv.d);
+    const size_t total = 2 * direct_buf_bytes(direct_chunk(B, single), pv.d);
     if (total > ws->blob_bytes) {
         if (ws->blob) { cudaDeviceSynchronize(); cudaFree(ws->blob); }
         ws->blob = nullptr; ws->blob_bytes = 0;
@@ -555,11 +587,12 @@ int launch_direct(const ProblemView& pv, DirectWorkspace** wsp, const double* ch
                   const ChunkHook* hook) {
     if (B <= 0) return QTET_OK;
     if (!direct_eligible(pv)) { set_error("direct path not eligible for this problem"); return QTET_EUNSUPPORTED; }
-    int rc = direct_reserve(pv, wsp, B);
+    if (n_dev && B > (1LL << 22)) { set_error("device-side batch size needs B <= 2^22"); return QTET_EINVAL; }
+    int rc = direct_reserve(pv, wsp, B, n_dev != nullptr);
     if (rc) return rc;
     DirectWorkspace* ws = *wsp;
     const int d = pv.d;
-    const long long chunk = direct_chunk(B);
+    const long long chunk = direct_chunk(B, n_dev != nullptr);
     const size_t buf_bytes = direct_buf_bytes(chunk, d);
     const size_t o_list = (((size_t)chunk * d * 8 + 255) / 256) * 256;
 
@@ -567,7 +600,6 @@ int launch_direct(const ProblemView& pv, DirectWorkspace** wsp, const double* ch
     a.pv = pv; a.site = site; a.acceptor = (site == pv.f - 1) ? 1 : 0;
     for (int k = 0; k < 32; ++k) { a.boff[k] = ws->boff[k]; a.iboff[k] = ws->iboff[k]; }
     a.n_dev = n_dev;                      // a device-side count only makes sense for a single chunk (the optimiser's case)
-    if (n_dev && B > chunk) { set_error("device-side batch size needs a single chunk"); return QTET_EINVAL; }
 
     QTET_CUDA(cudaEventRecord(ws->ev_fork, st));
     QTET_CUDA(cudaStreamWaitEvent(ws->aux, ws->ev_fork, 0));
@@ -585,7 +617,6 @@ int launch_direct(const ProblemView& pv, DirectWorkspace** wsp, const double* ch
         // K_E(c) on aux, after K_D(c-2) and its fallback released this buffer
         if (c >= 2) QTET_CUDA(cudaStreamWaitEvent(ws->aux, ws->ev_d[buf], 0));
         if (hook && hook->before) { const int hrc = hook->before(hook->ctx, lo, n, ws->aux); if (hrc) return hrc; }
-        QTET_CUDA(cudaMemsetAsync(a.fb_count, 0, sizeof(int), ws->aux));
         long long gridE = (long long)ws->sms * ws->per_sm_e;
         const long long needE = ((n + 31) / 32 + kWarpsE - 1) / kWarpsE;
         if (gridE > needE) gridE = needE;
