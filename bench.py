@@ -54,6 +54,11 @@ def make_points(w, rank=0):
     return np.ascontiguousarray(pts + rank * 1e-3)
 
 
+def checksum_sample_indices(n, count=4096):
+    """Seeded sample of the workload whose losses bench.py checks against the oracle after the timed region."""
+    return np.sort(np.random.default_rng(2).choice(n, size=min(count, n), replace=False))
+
+
 def algorithmic_flops(d, T, tridiagonal):
     # SURVEY.md §8(d): F = F_eigh + 4 T d^2 + 4 d^3 ; F_eigh = 6 d^3 (tridiagonal) / 9 d^3 (dense)
     return (6.0 if tridiagonal else 9.0) * d ** 3 + 4.0 * T * d ** 2 + 4.0 * d ** 3
@@ -254,6 +259,88 @@ def measure_secondary(_native, torch, dev, local, flush, peak, name="trimer10", 
     return res
 
 
+def run_solver_block(_native, torch, dev, local, rank, world, G=100000):
+    """BASELINE config 5: full qtet-style optimisation from G seeded random initial guesses, Adam + the reference's stop
+    rules (<= 1000 epochs, the 'bins' budget of solver_mp.py:149-152), the guesses sharded contiguously over the ranks
+    (STRONG scaling: G is fixed), and ONE collective: the NCCL all_gather of the per-rank arg-min records
+    (solver_mp.py:157-184).  Wall clock around the whole solve incl. the H2D of the guesses, max over ranks."""
+    import torch.distributed as dist
+    from tet import parallel
+    from tet.solver_mp import randomCombinations
+    N = 20
+    const = make_const(WORKLOADS["dimer20"])
+    lims = {"x0lims": [-10, 10], "x1lims": [-10, 10]}
+    combos = randomCombinations(lims, [0, 1], G, seed=0)
+    lo, hi = parallel.shard_bounds(G, rank, world)
+    prob = _native.Problem.from_const(const, device=local)
+    prob.reserve(hi - lo)
+    prob.adam_run(combos[lo:lo + 64], iterations=3)                                   # warm-up
+    parallel.global_argmin_device(prob, torch.zeros(1, 2, dtype=torch.float64, device=dev),
+                                  torch.zeros(1, dtype=torch.float64, device=dev), lo)  # communicator set-up
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    out = prob.adam_run(combos[lo:hi], train_sites=(0, 1), iterations=1000, lr=0.1)
+    idx, best = parallel.global_argmin_device(prob, out["best_vars"], out["best_loss"], lo)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    evals = float(out["epochs"].sum().item())
+    if world > 1:
+        t = torch.tensor([evals, dt], dtype=torch.float64, device=dev)
+        tot = t.clone(); dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        evals, dt = float(tot[0].item()), float(mx[1].item())
+    stats = prob.stats()
+    prob.close()
+    res = 6.0 / N
+    basin = bool(best[2] < 0.1 and abs(abs(best[0]) - res) < 0.05 and abs(abs(best[1]) - res) < 0.05 and best[0] * best[1] < 0)
+    return {"config": f"dimer N={N}, {G} uniform random guesses in [-10,10]^2 (seed 0), Adam lr=0.1, <=1000 epochs, "
+                      f"sharded over {world} GPU(s), NCCL arg-min", "scaling": "strong", "wall_s": dt,
+            "loss_grad_evals": int(evals), "evals_per_s": evals / dt, "best_loss": float(best[2]),
+            "best_chis": [float(best[0]), float(best[1])], "best_index": int(idx), "resonance_chi": res,
+            "basin_ok": basin, "epochs_run": int(out["epochs_run"]), "kernel_stats": stats}
+
+
+def run_config3_block(_native, torch, dev, local, rank, world, flush, peak, total=1 << 18, steps=3, warmup=3):
+    """BASELINE config 3: dimer N=100 (d = 101), 2^18 seeded points in total, contiguous shards over the ranks (strong
+    scaling, no collective on the data path); device-timed, max over ranks."""
+    import torch.distributed as dist
+    from tet import parallel
+    w = WORKLOADS["dimer100"]
+    const = make_const(w)
+    pts = np.random.default_rng(0).uniform(-10, 10, (total, 2))
+    lo, hi = parallel.shard_bounds(total, rank, world)
+    prob = _native.Problem.from_const(const, device=local)
+    chis = torch.from_numpy(pts[lo:hi]).to(dev)
+    n = hi - lo
+    out = (torch.empty(n, dtype=torch.float64, device=dev), torch.empty(n, 2, dtype=torch.float64, device=dev),
+           torch.empty(n, dtype=torch.int32, device=dev))
+    for _ in range(warmup):
+        prob.loss_grad(chis, out=out)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
+        flush.zero_()
+        ev[i][0].record(); prob.loss_grad(chis, out=out); ev[i][1].record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    F = algorithmic_flops(prob.dim, const["timesteps"], True)
+    rate = total / (ms * 1e-3)
+    stats = prob.stats()
+    prob.close()
+    return {"config": f"dimer N=100, {total} uniform points in [-10,10]^2 (seed 0) sharded over {world} GPU(s)",
+            "scaling": "strong", "value": rate, "unit": "evals/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+            "flops_per_eval": F, "roofline_frac_per_gpu": (rate / world * F / 1e12 / peak) if peak else None,
+            "kernel_stats": stats}
+
+
 # --------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -265,6 +352,7 @@ def main():
     ap.add_argument("--path", default="auto", choices=["auto", "generic", "split", "direct"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the trimer N=10 side measurement of the default run")
+    ap.add_argument("--no-solver", action="store_true", help="skip the config-5 (sharded optimisation + NCCL arg-min) and config-3 blocks")
     ap.add_argument("--points", type=int, default=0, help="override the number of points per GPU (random workloads: any size; grid: truncation)")
     args = ap.parse_args()
     if args.impl == "ours":
@@ -286,9 +374,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the QTET B200 path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        # keep stdout to the single JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION/INFO
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries the single JSON line; NCCL's own log (whatever NCCL_DEBUG the launcher chose) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
@@ -378,14 +465,31 @@ def main():
         e2e_s = float(t.item())
     e2e_value = world * B * args.steps / e2e_s
     checksum = float(h_loss.sum())
+    kstats = prob.stats()
+
+    # ---- blocks every rank takes part in (outside the timed regions above): config 5 and config 3
+    solver = config3 = None
+    peak = peaks2 = None
+    try:
+        peaks2 = _native.fp64_peaks_tflops(local, 0.6)
+        peak = max(peaks2.values())
+    except Exception:
+        pass
+    if args.workload == "dimer20" and not args.no_solver and not args.points:
+        solver = run_solver_block(_native, torch, dev, local, rank, world)
+        config3 = run_config3_block(_native, torch, dev, local, rank, world, flush, peak)
 
     if rank == 0:
         d = prob.dim
         F = algorithmic_flops(d, const["timesteps"], tridiagonal=(f == 2))
-        try:
-            peak = _native.fp64_peak_tflops(local, 0.5)
-        except Exception:
-            peak = None
+        # the losses the e2e call brought back, checked against the oracle on a seeded sample of THIS workload
+        idx = checksum_sample_indices(B)
+        from oracle import qtet_oracle as _O
+        L_ref = np.concatenate([_O.loss_grad_batch(const, pts_host[idx[lo:lo + 1024]], f - 1)[0] for lo in range(0, len(idx), 1024)])
+        L_got = h_loss.numpy()[idx]
+        chk = {"points": int(len(idx)), "max_abs_diff": float(np.abs(L_got - L_ref).max()),
+               "sum_diff": float(abs(L_got.sum() - L_ref.sum())), "tolerance": 1e-10 * const["max_N"]}
+        chk["ok"] = bool(chk["max_abs_diff"] <= chk["tolerance"] * (10.0 if const["max_N"] > 31 else 1.0))
         per_gpu_rate = B * args.steps / (total_ms * 1e-3)
         # dominant kernel: algorithmic flops of the points one launch processes / its average launch duration
         kms = {k: v for k, v in kern.items() if v[1] > 0}
@@ -397,12 +501,14 @@ def main():
             achieved = (dpts / dn) * F / (dms / dn * 1e-3) / 1e12
         else:
             achieved = per_gpu_rate * F / 1e12
-        traffic = None
+        traffic = traffic_source = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
                 tj = json.load(fh)
-            if dom in tj and tj[dom].get("workload") == args.workload:
-                traffic = tj[dom]["dram_bytes_per_point"] * (kms[dom][2] / kms[dom][1])
+            key = f"{args.workload}/{path_name}/{dom}"
+            if key in tj:                          # DRAM bytes per point from an `ncu --set full` capture of this workload + path
+                traffic = tj[key]["dram_bytes_per_point"] * (kms[dom][2] / kms[dom][1])
+                traffic_source = tj[key]["source"]
         except Exception:
             pass
         peaks = {}
@@ -413,10 +519,11 @@ def main():
             pass
         hbm_bytes = (8 * f) + 8 * (1 + f) + 4
         roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": (achieved / peak) if peak else None, "traffic": traffic,
+                    "frac": (achieved / peak) if peak else None, "traffic": traffic, "traffic_source": traffic_source,
                     "flops_per_eval": F, "kernel": dom, "kernels": kernels,
                     "whole_step": {"achieved": per_gpu_rate * F / 1e12, "frac": (per_gpu_rate * F / 1e12 / peak) if peak else None},
-                    "peak_source": "FP64 DFMA micro-benchmark run inside this bench (MEASURED_PEAKS.json has no FP64 figure)",
+                    "peak_source": "max of the FP64 DFMA and DMMA (mma.sync m8n8k4) micro-benchmarks run inside this bench "
+                                   "(MEASURED_PEAKS.json has no FP64 figure)", "peaks_measured": peaks2,
                     "kernel_path": path_name,
                     "hbm": {"algorithmic_bytes_per_eval": hbm_bytes, "achieved_GBps": per_gpu_rate * hbm_bytes / 1e9,
                             "peak_GBps": peaks.get("hbm_gbs"), "frac": (per_gpu_rate * hbm_bytes / 1e9 / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None}}
@@ -442,11 +549,18 @@ def main():
                 "config": {"workload": w["label"], "points_per_gpu": B, "fock_dim": d, "timesteps": const["timesteps"],
                            "target_site": "acceptor", "kernel_path": path_name,
                            "l2": "256 MiB buffer written between timed iterations (L2 flush)"},
-                "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary,
+                "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary, "solver": solver, "config3": config3,
                 "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(B * f * 8),
-                        "d2h_bytes_per_step": int(B * (8 + 8 * f + 4)), "checksum_loss_sum": checksum},
-                "gpu_launches": int(launches), "clocks": clocks}
+                        "d2h_bytes_per_step": int(B * (8 + 8 * f + 4)), "checksum_loss_sum": checksum,
+                        "checksum_check": chk},
+                "kernel_stats": kstats, "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(line), flush=True)
+        if not chk["ok"]:
+            raise SystemExit(f"bench.py: losses differ from the oracle on the checksum sample: {chk}")
+        if kstats["nonconverged"]:
+            raise SystemExit(f"bench.py: {kstats['nonconverged']} eigen-solves did not converge")
+        if solver is not None and not solver["basin_ok"]:
+            raise SystemExit(f"bench.py: the sharded optimisation missed the +-6/N resonance basin: {solver}")
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

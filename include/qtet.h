@@ -66,6 +66,14 @@ int qtet_problem_time_grid(const qtet_problem* p, double* t_host);
  * buffer (Loss.createHamiltonian, HamiltonianLoss.py:168-176).  Parity/debug aid. */
 int qtet_hamiltonian_host(qtet_problem* p, const double* chis_host, double* H_host);
 
+/*
+ * Size the handle's workspaces for batches of up to B points NOW.  After it, qtet_loss_grad / qtet_trace / qtet_adam_run
+ * with batches <= B on the direct path neither allocate nor synchronise (they are purely asynchronous on the caller's
+ * stream, as the conventions above promise); without it a workspace grows on the first call that needs more room, and
+ * growing means cudaDeviceSynchronize + cudaFree + cudaMalloc.  The split / large-d paths size theirs on first use.
+ */
+int qtet_problem_reserve(qtet_problem* p, int64_t B);
+
 /* Choose the kernel family (QTET_PATH_*); QTET_EUNSUPPORTED if the problem is not eligible. */
 int qtet_set_path(qtet_problem* p, int path);
 /* Which family the next call will use (QTET_PATH_GENERIC, QTET_PATH_SPLIT or QTET_PATH_DIRECT). */
@@ -117,9 +125,11 @@ int qtet_adam_run(qtet_problem* p, double* chis_dev, int64_t B, int target_site,
  * double-encoded int64 bit pattern is avoided: index is written to idx_dev).  First minimum wins. */
 int qtet_argmin(const double* values_dev, int64_t B, double* min_dev, int64_t* idx_dev, void* stream);
 
-/* Measured FP64 FMA throughput of the device (dependent-free DFMA loop), TFLOP/s.  Used as the
- * roofline denominator because MEASURED_PEAKS.json carries no FP64 figure. */
+/* Measured FP64 throughput of the device, TFLOP/s: the higher of a dependent-free DFMA loop and an mma.sync m8n8k4 (FP64
+ * tensor path, DMMA) loop.  Used as the roofline denominator because MEASURED_PEAKS.json carries no FP64 figure.
+ * qtet_fp64_peak2 returns both figures. */
 int qtet_fp64_peak(int device, double seconds_budget, double* tflops_out);
+int qtet_fp64_peak2(int device, double seconds_budget, double* dfma_tflops_out, double* dmma_tflops_out);
 
 /* Per-kernel timing (CUDA events on the launching streams).  kind 0: scalar QL kernel, 1: rotation-replay /
  * evolution / gradient kernel (the dominant one), 2: fused generic kernel, or the
@@ -128,6 +138,13 @@ int qtet_fp64_peak(int device, double seconds_budget, double* tflops_out);
  * the number of parameter points they processed (arrays of 3). */
 int qtet_profile_enable(qtet_problem* p, int on);
 int qtet_profile_read(qtet_problem* p, double* ms_sum, int64_t* launches, int64_t* points);
+
+/* Cumulative health counters of the handle's kernels (synchronises the device): out4[0] = points the direct path handed to
+ * the fused generic kernel (numerically degenerate spectrum, recurrence overflow, QL not converged), out4[1] = points whose
+ * rotation stream overflowed on the split paths (also recomputed by the generic kernel), out4[2] = eigen-solves of the
+ * generic kernel that hit its iteration limit -- the only case in which a result may be inaccurate; tests and bench.py
+ * assert it is 0 -- out4[3] reserved.  reset != 0 clears the counters. */
+int qtet_stats(qtet_problem* p, int64_t* out4, int reset);
 
 /* Number of kernel launches this library has issued in the calling process so far. */
 int64_t qtet_launch_count(void);

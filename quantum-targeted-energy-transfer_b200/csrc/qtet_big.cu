@@ -281,6 +281,7 @@ __global__ void __launch_bounds__(kWarpsBig * 32) ql_scalar_big_kernel(BigQlArgs
             if (overflow) {
                 const int slot = atomicAdd(a.overflow_count, 1);
                 a.overflow_list[slot] = (int)p;
+                atomicAdd(a.pv.stats + 1, 1ULL);
             }
             for (int m = 0; m < d; ++m) a.bs.ev[p * d + m] = t.dg(m);
         }

@@ -88,7 +88,7 @@ int qtet_problem_create(int max_N, int sites, const double* omegas, double coupl
         enumerate_states(max_N, sites, cur, 0, max_N, st);
     }
     const int d = (int)st.size();
-    QTET_CUDA(cudaSetDevice(device));
+    QTET_ON_DEVICE(device);
 
     qtet_problem* p = new (std::nothrow) qtet_problem();
     if (!p) { set_error("out of host memory"); return QTET_ENOMEM; }
@@ -155,6 +155,8 @@ int qtet_problem_create(int max_N, int sites, const double* omegas, double coupl
     }
     const size_t o_lin = push(lin), o_quad = push(quad), o_occ = push(p->states), o_off = push(offd),
                  o_t = push(p->tgrid), o_om = push(p->omegas);
+    const size_t o_stats = blob.size();
+    blob.resize(blob.size() + 4, 0.0);            // 4 x uint64 counters (all-zero bit pattern)
     cudaError_t e = cudaMalloc(&p->dev_blob, blob.size() * sizeof(double));
     if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaMalloc(constants)"); }
     e = cudaMemcpy(p->dev_blob, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice);
@@ -163,6 +165,7 @@ int qtet_problem_create(int max_N, int sites, const double* omegas, double coupl
     v.N = max_N; v.f = sites; v.d = d; v.T = timesteps; v.tridiag = p->tridiag ? 1 : 0; v.offd_nonzero = offd_nonzero ? 1 : 0; v.max_t = max_t;
     v.lin = p->dev_blob + o_lin; v.quad = p->dev_blob + o_quad; v.occ = p->dev_blob + o_occ;
     v.offd = p->dev_blob + o_off; v.tgrid = p->dev_blob + o_t; v.omegas = p->dev_blob + o_om;
+    v.stats = reinterpret_cast<unsigned long long*>(p->dev_blob + o_stats);
     p->path = auto_path(v);
     *out = p;
     return QTET_OK;
@@ -170,7 +173,7 @@ int qtet_problem_create(int max_N, int sites, const double* omegas, double coupl
 
 void qtet_problem_destroy(qtet_problem* p) {
     if (!p) return;
-    cudaSetDevice(p->device);
+    DeviceGuard _guard(p->device);
     if (p->dev_blob) cudaFree(p->dev_blob);
     if (p->scratch) cudaFree(p->scratch);
     if (p->s_in) cudaStreamDestroy(p->s_in);
@@ -227,6 +230,20 @@ int qtet_set_path(qtet_problem* p, int path) {
 
 int qtet_get_path(const qtet_problem* p) { return p ? p->path : QTET_EINVAL; }
 
+int qtet_problem_reserve(qtet_problem* p, int64_t B) {
+    if (!p || B < 0) { set_error("bad argument"); return QTET_EINVAL; }
+    QTET_ON_DEVICE(p->device);
+    const size_t f = p->f;
+    // scratch of the *_host entry point and of the optimiser (the larger of the two layouts)
+    const size_t host_call = (size_t)B * (2 * f + 1) * 8 + (size_t)B * 4 + 64;
+    const size_t adam = (size_t)B * (5 * f * 8 + 3 * 8 + f * 4 + 4 * 4) + 16 * 256;
+    int rc = ensure_scratch(p, host_call > adam ? host_call : adam);
+    if (rc) return rc;
+    if (p->path == QTET_PATH_DIRECT && B <= (1LL << 22)) return direct_reserve(p->view, &p->direct_ws, B, true);
+    if (p->path == QTET_PATH_DIRECT) return direct_reserve(p->view, &p->direct_ws, B, false);
+    return QTET_OK;
+}
+
 static int check_call(qtet_problem* p, const void* chis, int64_t B, int site) {
     if (!p) { set_error("null handle"); return QTET_EINVAL; }
     if (B < 0) { set_error("negative batch"); return QTET_EINVAL; }
@@ -241,7 +258,7 @@ int qtet_loss_grad(qtet_problem* p, const double* chis_dev, int64_t B, int targe
     if (rc) return rc;
     if (B == 0) return QTET_OK;
     if (!loss_dev) { set_error("loss is NULL"); return QTET_EINVAL; }
-    QTET_CUDA(cudaSetDevice(p->device));
+    QTET_ON_DEVICE(p->device);
     return loss_grad_dispatch(p, chis_dev, B, target_site, loss_dev, grad_dev, tstar_dev, nullptr, (cudaStream_t)stream);
 }
 
@@ -250,7 +267,7 @@ int qtet_trace(qtet_problem* p, const double* chis_dev, int64_t B, int target_si
     if (rc) return rc;
     if (B == 0) return QTET_OK;
     if (!trace_dev) { set_error("trace is NULL"); return QTET_EINVAL; }
-    QTET_CUDA(cudaSetDevice(p->device));
+    QTET_ON_DEVICE(p->device);
     return loss_grad_dispatch(p, chis_dev, B, target_site, nullptr, nullptr, nullptr, trace_dev, (cudaStream_t)stream);
 }
 
@@ -260,7 +277,7 @@ int qtet_loss_grad_host(qtet_problem* p, const double* chis_host, int64_t B, int
     if (rc) return rc;
     if (B == 0) return QTET_OK;
     if (!loss_host) { set_error("loss is NULL"); return QTET_EINVAL; }
-    QTET_CUDA(cudaSetDevice(p->device));
+    QTET_ON_DEVICE(p->device);
     const size_t f = p->f;
     const size_t nb_chi = (size_t)B * f * 8, nb_loss = (size_t)B * 8, nb_grad = (size_t)B * f * 8, nb_t = (size_t)B * 4;
     rc = ensure_scratch(p, nb_chi + nb_loss + nb_grad + nb_t + 64);
@@ -328,7 +345,7 @@ int qtet_loss_grad_host(qtet_problem* p, const double* chis_host, int64_t B, int
 
 int qtet_hamiltonian_host(qtet_problem* p, const double* chis_host, double* H_host) {
     if (!p || !chis_host || !H_host) { set_error("null argument"); return QTET_EINVAL; }
-    QTET_CUDA(cudaSetDevice(p->device));
+    QTET_ON_DEVICE(p->device);
     const size_t nH = (size_t)p->d * p->d * 8, nchi = (size_t)p->f * 8;
     int rc = ensure_scratch(p, nH + nchi + 64);
     if (rc) return rc;
@@ -343,12 +360,16 @@ int qtet_hamiltonian_host(qtet_problem* p, const double* chis_host, double* H_ho
 
 int qtet_argmin(const double* values_dev, int64_t B, double* min_dev, int64_t* idx_dev, void* stream) {
     if (B <= 0 || !values_dev || !min_dev || !idx_dev) { set_error("bad argument"); return QTET_EINVAL; }
+    cudaPointerAttributes attr{};
+    QTET_CUDA(cudaPointerGetAttributes(&attr, values_dev));
+    if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged) { set_error("values_dev is not device memory"); return QTET_EINVAL; }
+    QTET_ON_DEVICE(attr.device);                 // launch where the data lives, whatever the caller's current device is
     return launch_argmin(values_dev, B, min_dev, idx_dev, (cudaStream_t)stream);
 }
 
 int qtet_profile_enable(qtet_problem* p, int on) {
     if (!p) { set_error("null handle"); return QTET_EINVAL; }
-    QTET_CUDA(cudaSetDevice(p->device));
+    QTET_ON_DEVICE(p->device);
     QTET_CUDA(cudaDeviceSynchronize());
     p->prof.clear();
     p->prof.on = on != 0;
@@ -357,7 +378,7 @@ int qtet_profile_enable(qtet_problem* p, int on) {
 
 int qtet_profile_read(qtet_problem* p, double* ms_sum, int64_t* launches, int64_t* points) {
     if (!p || !ms_sum || !launches || !points) { set_error("null argument"); return QTET_EINVAL; }
-    QTET_CUDA(cudaSetDevice(p->device));
+    QTET_ON_DEVICE(p->device);
     QTET_CUDA(cudaDeviceSynchronize());
     for (int k = 0; k < Profiler::kKinds; ++k) {
         ms_sum[k] = 0.0; launches[k] = 0; points[k] = 0;
@@ -368,6 +389,17 @@ int qtet_profile_read(qtet_problem* p, double* ms_sum, int64_t* launches, int64_
             } else cudaGetLastError();
         }
     }
+    return QTET_OK;
+}
+
+int qtet_stats(qtet_problem* p, int64_t* out4, int reset) {
+    if (!p || !out4) { set_error("null argument"); return QTET_EINVAL; }
+    QTET_ON_DEVICE(p->device);
+    QTET_CUDA(cudaDeviceSynchronize());
+    unsigned long long h[4] = {0, 0, 0, 0};
+    QTET_CUDA(cudaMemcpy(h, p->view.stats, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; ++i) out4[i] = (int64_t)h[i];
+    if (reset) QTET_CUDA(cudaMemset(p->view.stats, 0, sizeof(h)));
     return QTET_OK;
 }
 

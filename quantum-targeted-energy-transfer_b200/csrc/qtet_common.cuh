@@ -21,6 +21,8 @@ struct ProblemView {
     const double* offd;   // tridiag: [d-1] H[m+1,m]; dense: [d, d] hopping part   :136-163
     const double* tgrid;  // [T]     linspace(0, max_t, T)                HamiltonianLoss.py:221
     const double* omegas; // [f]
+    unsigned long long* stats;   // [4] cumulative counters: 0 direct-path points sent to the generic kernel, 1 rotation-stream
+                                 //     overflows (split paths), 2 eigen-solves that hit the iteration limit, 3 reserved
 };
 
 void set_error(const std::string& msg);
@@ -34,6 +36,24 @@ void count_launch(int n = 1);
     } while (0)
 
 struct Profiler;
+
+// Entry points switch to the handle's device and give the caller's current device back on return (a process may hold
+// handles on several devices, or have torch's current device elsewhere).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) err = cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+#define QTET_ON_DEVICE(dev)                                   \
+    DeviceGuard _guard(dev);                                  \
+    if (_guard.err != cudaSuccess) return cuda_fail(_guard.err, "cudaSetDevice")
 
 // ---- launchers implemented in the kernel translation units -------------------------------
 int launch_generic(const ProblemView& pv, const double* chis, int64_t B, int site, double* loss,

@@ -153,14 +153,15 @@ struct DLayout {
 // ------------------------------------------------------------------------------------------------
 // K_D: G lanes per point; eigenvectors by two-sided recurrences, then the shared phases.
 // ------------------------------------------------------------------------------------------------
-template <int D, int G, int WARPS, int MINB>
+// EXACT: the Fock dimension equals the template size (no padded rows / eigen-indices), d is a compile-time constant.
+template <int D, int G, int WARPS, int MINB, bool EXACT>
 __global__ void __launch_bounds__(WARPS * 32, MINB) direct_kernel(SplitArgs a) {
     using L = BLayout<D, G>;
     using DL = DLayout<D, G>;
     constexpr int R = L::R, RZ = L::RZ, PPW = L::PPW, LDV = DL::LDV;
     extern __shared__ double sm[];
     const ProblemView& pv = a.pv;
-    const int d = pv.d, f = pv.f, T = pv.T;
+    const int d = EXACT ? D : pv.d, f = pv.f, T = pv.T;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / G, q = lane % G;
     // CTA-wide constants
@@ -251,6 +252,17 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) direct_kernel(SplitArgs a) {
         double* colp[RZ];
 #pragma unroll
         for (int t = 0; t < RZ; ++t) { const int i = q + t * G; colp[t] = vp + ((i < D) ? i : (D - 1)); }   // i >= D: nothing is stored
+        // Diagonal and hopping constants in registers for the three passes: with two warps per scheduler nothing hides a
+        // load that sits right in front of its use, and phase 0 holds no other large state.  The loads are volatile asm so
+        // that they stay up here instead of being re-materialised next to each use.
+        double av[D], bv[D], ibv[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const unsigned addr = (unsigned)__cvta_generic_to_shared(ap + k);
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(av[k]) : "r"(addr));
+            bv[k] = a.boff[k]; ibv[k] = a.iboff[k];
+        }
+        PHASE_MARK(10);
         // from the bottom: q_{k-1} = ((lam - a_k) q_k - b_k q_{k+1}) / b_{k-1},  q_{d-1} = 1
         {
             double qn[RZ], qc[RZ];
@@ -261,7 +273,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) direct_kernel(SplitArgs a) {
             }
 #pragma unroll
             for (int k = D - 1; k >= 1; --k) {
-                const double bk = a.boff[k], ibm = a.iboff[k - 1], ak = ap[k];
+                const double bk = bv[k], ibm = ibv[k - 1], ak = av[k];
 #pragma unroll
                 for (int t = 0; t < RZ; ++t) {
                     double val = fma(lam[t] - ak, qc[t], -(bk * qn[t])) * ibm;
@@ -272,6 +284,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) direct_kernel(SplitArgs a) {
             }
         }
         __syncwarp();
+        PHASE_MARK(11);
         // from the top: p_{k+1} = ((lam - a_k) p_k - b_{k-1} p_{k-1}) / b_k,  p_0 = 1; join row r = argmax |p_k q_k|
         double invp[RZ], invq[RZ];
         int rj[RZ];
@@ -284,7 +297,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) direct_kernel(SplitArgs a) {
             }
 #pragma unroll
             for (int k = 0; k < D - 1; ++k) {
-                const double bm = (k >= 1) ? a.boff[k - 1] : 0.0, ib = a.iboff[k], ak = ap[k];
+                const double bm = (k >= 1) ? bv[k - 1] : 0.0, ib = ibv[k], ak = av[k];
 #pragma unroll
                 for (int t = 0; t < RZ; ++t) {
                     const double qk1 = colp[t][(k + 1) * LDV];
@@ -297,6 +310,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) direct_kernel(SplitArgs a) {
 #pragma unroll
             for (int t = 0; t < RZ; ++t) { invp[t] = fast_rcp(pr[t]); invq[t] = fast_rcp(qr[t]); }
         }
+        PHASE_MARK(12);
         // second pass from the top: z_k = p_k / p_r above the join, q_k / q_r from the join down; 1 / |z| goes to rnbuf
         // (the scale is applied when the rows are read back)
         {
@@ -305,7 +319,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) direct_kernel(SplitArgs a) {
             for (int t = 0; t < RZ; ++t) { pm[t] = 0.0; pcur[t] = 1.0; ss[t] = 0.0; }
 #pragma unroll
             for (int k = 0; k < D; ++k) {
-                const double bm = (k >= 1) ? a.boff[k - 1] : 0.0, ib = a.iboff[k], ak = ap[k];
+                const double bm = (k >= 1) ? bv[k - 1] : 0.0, ib = ibv[k], ak = av[k];
 #pragma unroll
                 for (int t = 0; t < RZ; ++t) {
                     const int i = q + t * G;
@@ -383,6 +397,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) direct_kernel(SplitArgs a) {
             if (fbi && q == 0 && valid) {
                 const int slot = atomicAdd(a.fb_count, 1);
                 a.fb_list[slot] = (int)p;
+                atomicAdd(pv.stats + 0, 1ULL);
             }
         }
         // ---- order the eigen-indices by |c_i| = |V[0][i]| descending (ties by index): rank of my own indices against all
@@ -438,11 +453,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) direct_kernel(SplitArgs a) {
 
 struct KernelCfg { int per_sm = 0; size_t smem = 0; };
 
-template <int D, int G, int WARPS, int MINB>
+template <int D, int G, int WARPS, int MINB, bool EXACT>
 int config_direct(KernelCfg& cfg) {
     using DL = DLayout<D, G>;
     cfg.smem = ((size_t)DL::CONSTS + (size_t)DL::PER_WARP * WARPS) * sizeof(double);
-    auto kern = direct_kernel<D, G, WARPS, MINB>;
+    auto kern = direct_kernel<D, G, WARPS, MINB, EXACT>;
     QTET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
     QTET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     QTET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.per_sm, kern, WARPS * 32, cfg.smem));
@@ -451,14 +466,14 @@ int config_direct(KernelCfg& cfg) {
     return QTET_OK;
 }
 
-template <int D, int G, int WARPS, int MINB>
+template <int D, int G, int WARPS, int MINB, bool EXACT>
 int launch_direct_kernel(const SplitArgs& a, const KernelCfg& cfg, int sms, cudaStream_t st) {
     using L = BLayout<D, G>;
     long long grid = (long long)sms * cfg.per_sm;
     const long long ntask = (a.n + L::PPW - 1) / L::PPW;
     const long long need = (ntask + WARPS - 1) / WARPS;
     if (grid > need) grid = need;
-    direct_kernel<D, G, WARPS, MINB><<<(unsigned)grid, WARPS * 32, cfg.smem, st>>>(a);
+    direct_kernel<D, G, WARPS, MINB, EXACT><<<(unsigned)grid, WARPS * 32, cfg.smem, st>>>(a);
     count_launch();
     QTET_CUDA(cudaGetLastError());
     return QTET_OK;
@@ -526,12 +541,12 @@ static int direct_workspace_init(const ProblemView& pv, DirectWorkspace** wsp) {
     }
     int rc;
     switch (ws->D) {
-        case 4: rc = config_direct<4, 4, 4, 4>(ws->cfg_d); break;
-        case 8: rc = config_direct<8, 8, 4, 4>(ws->cfg_d); break;
-        case 16: rc = config_direct<16, 8, 2, 6>(ws->cfg_d); break;
-        case 21: rc = config_direct<21, 8, 2, 4>(ws->cfg_d); break;
-        case 24: rc = config_direct<24, 8, 2, 4>(ws->cfg_d); break;
-        default: rc = config_direct<32, 16, 2, 4>(ws->cfg_d); break;
+        case 4: rc = config_direct<4, 4, 4, 4, false>(ws->cfg_d); break;
+        case 8: rc = config_direct<8, 8, 4, 4, false>(ws->cfg_d); break;
+        case 16: rc = config_direct<16, 8, 2, 6, false>(ws->cfg_d); break;
+        case 21: rc = (pv.d == 21) ? config_direct<21, 8, 2, 4, true>(ws->cfg_d) : config_direct<21, 8, 2, 4, false>(ws->cfg_d); break;
+        case 24: rc = config_direct<24, 8, 2, 4, false>(ws->cfg_d); break;
+        default: rc = config_direct<32, 16, 2, 4, false>(ws->cfg_d); break;
     }
     if (rc) return rc;
     ws->smem_e = (size_t)kWarpsE * 2 * pv.d * 32 * sizeof(double);
@@ -630,12 +645,13 @@ int launch_direct(const ProblemView& pv, DirectWorkspace** wsp, const double* ch
         QTET_CUDA(cudaStreamWaitEvent(st, ws->ev_e[buf], 0));
         if (prof) prof->begin(1, n, st);
         switch (ws->D) {
-            case 4: rc = launch_direct_kernel<4, 4, 4, 4>(a, ws->cfg_d, ws->sms, st); break;
-            case 8: rc = launch_direct_kernel<8, 8, 4, 4>(a, ws->cfg_d, ws->sms, st); break;
-            case 16: rc = launch_direct_kernel<16, 8, 2, 6>(a, ws->cfg_d, ws->sms, st); break;
-            case 21: rc = launch_direct_kernel<21, 8, 2, 4>(a, ws->cfg_d, ws->sms, st); break;
-            case 24: rc = launch_direct_kernel<24, 8, 2, 4>(a, ws->cfg_d, ws->sms, st); break;
-            default: rc = launch_direct_kernel<32, 16, 2, 4>(a, ws->cfg_d, ws->sms, st); break;
+            case 4: rc = launch_direct_kernel<4, 4, 4, 4, false>(a, ws->cfg_d, ws->sms, st); break;
+            case 8: rc = launch_direct_kernel<8, 8, 4, 4, false>(a, ws->cfg_d, ws->sms, st); break;
+            case 16: rc = launch_direct_kernel<16, 8, 2, 6, false>(a, ws->cfg_d, ws->sms, st); break;
+            case 21: rc = (d == 21) ? launch_direct_kernel<21, 8, 2, 4, true>(a, ws->cfg_d, ws->sms, st)
+                                   : launch_direct_kernel<21, 8, 2, 4, false>(a, ws->cfg_d, ws->sms, st); break;
+            case 24: rc = launch_direct_kernel<24, 8, 2, 4, false>(a, ws->cfg_d, ws->sms, st); break;
+            default: rc = launch_direct_kernel<32, 16, 2, 4, false>(a, ws->cfg_d, ws->sms, st); break;
         }
         if (prof) prof->finish(1, st);
         if (rc) return rc;

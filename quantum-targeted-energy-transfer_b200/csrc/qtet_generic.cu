@@ -268,7 +268,7 @@ __global__ void generic_kernel(GenericArgs a) {
                         if (fabs(of[m]) <= kEps * dd) break;
                     }
                     if (m == l) break;
-                    if (++iter > kMaxQlIter) break;
+                    if (++iter > kMaxQlIter) { if (tid == 0) atomicAdd(pv.stats + 2, 1ULL); break; }   // surfaced through qtet_stats
                     double g = (dg[l + 1] - dg[l]) / (2.0 * of[l]);
                     double r = sqrt(g * g + 1.0);
                     g = dg[m] - dg[l] + of[l] / (g + copysign(r, g));

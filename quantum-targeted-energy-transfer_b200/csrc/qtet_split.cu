@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(kWarpsA * 32) ql_scalar_kernel(SplitArgs a) {
             if (overflow) {
                 const int slot = atomicAdd(a.overflow_count, 1);
                 a.overflow_list[slot] = (int)p;
+                atomicAdd(pv.stats + 1, 1ULL);
             }
             for (int m = 0; m < d; ++m) a.ev[p * d + m] = t.dg(m);
         }

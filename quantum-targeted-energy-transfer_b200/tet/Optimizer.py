@@ -199,7 +199,7 @@ def mp_opt(i: int, combination: list, iteration_path: str, const: dict, target_s
 
 
 def mp_opt_batch(combinations, iteration_path, const, target_site, iterations, lr, beta_1, amsgrad_bool,
-                 write_data, train_sites, first_index=0, problem=None, quiet=False):
+                 write_data, train_sites, first_index=0, problem=None, quiet=False, on_device=False):
     """All guesses of one solver iteration in ONE device batch (replaces pool.starmap_async(mp_opt, args),
     solver_mp.py:157-172).  Returns the [G, f+1] array solver_mp.py:182 builds from the pool results."""
     f = len(const['chis'])
@@ -208,10 +208,16 @@ def mp_opt_batch(combinations, iteration_path, const, target_site, iterations, l
     x0 = np.zeros((G, f))                                  # Optimizer.py:307-312
     for col, site in enumerate(train_sites):
         x0[:, site] = combos[:, col]
+    own = problem is None
     prob = problem if problem is not None else _native.Problem.from_const(const)
     out = prob.adam_run(x0, site=prob._site(target_site), train_sites=train_sites, iterations=iterations,
                         lr=lr, beta_1=beta_1, amsgrad=amsgrad_bool, tol=TensorflowParams['tol'],
                         history=bool(write_data))
+    if on_device and not write_data:
+        # large shards: the results stay on the GPU, the caller reduces them there (parallel.global_argmin_device)
+        if own:
+            prob.close()
+        return out['best_vars'], out['best_loss']
     best = out['best_vars'].cpu().numpy()
     best_loss = out['best_loss'].cpu().numpy()
     if write_data:
@@ -227,4 +233,6 @@ def mp_opt_batch(combinations, iteration_path, const, target_site, iterations, l
     if not quiet:
         for g in range(G):
             print(f'Job {first_index + g}: Done')          # Optimizer.py:319
+    if own:
+        prob.close()
     return np.concatenate([best, best_loss[:, None]], axis=1)

@@ -39,6 +39,7 @@ def _load():
         "qtet_problem_states": (C.c_int, [P, D]),
         "qtet_problem_time_grid": (C.c_int, [P, D]),
         "qtet_hamiltonian_host": (C.c_int, [P, D, D]),
+        "qtet_problem_reserve": (C.c_int, [P, C.c_int64]),
         "qtet_set_path": (C.c_int, [P, C.c_int]),
         "qtet_get_path": (C.c_int, [P]),
         "qtet_loss_grad": (C.c_int, [P, P, C.c_int64, C.c_int, P, P, P, P]),
@@ -48,8 +49,10 @@ def _load():
                                     C.c_double, C.c_double, C.c_int, C.c_double, P, P, P, P, P, P]),
         "qtet_argmin": (C.c_int, [P, C.c_int64, P, P, P]),
         "qtet_fp64_peak": (C.c_int, [C.c_int, C.c_double, D]),
+        "qtet_fp64_peak2": (C.c_int, [C.c_int, C.c_double, D, D]),
         "qtet_profile_enable": (C.c_int, [P, C.c_int]),
         "qtet_profile_read": (C.c_int, [P, D, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+        "qtet_stats": (C.c_int, [P, C.POINTER(C.c_int64), C.c_int]),
         "qtet_launch_count": (C.c_int64, []),
         "qtet_last_error": (C.c_char_p, []),
         "qtet_version": (C.c_char_p, []),
@@ -63,9 +66,9 @@ def _load():
 
 lib = _load()
 EXPORTS = ["qtet_problem_create", "qtet_problem_destroy", "qtet_problem_dim", "qtet_problem_states",
-           "qtet_problem_time_grid", "qtet_hamiltonian_host", "qtet_set_path", "qtet_get_path",
+           "qtet_problem_time_grid", "qtet_hamiltonian_host", "qtet_problem_reserve", "qtet_set_path", "qtet_get_path",
            "qtet_loss_grad", "qtet_loss_grad_host", "qtet_trace", "qtet_adam_run", "qtet_argmin",
-           "qtet_fp64_peak", "qtet_profile_enable", "qtet_profile_read", "qtet_launch_count", "qtet_last_error",
+           "qtet_fp64_peak", "qtet_fp64_peak2", "qtet_profile_enable", "qtet_profile_read", "qtet_stats", "qtet_launch_count", "qtet_last_error",
            "qtet_version"]
 
 
@@ -91,6 +94,14 @@ def fp64_peak_tflops(device: int = 0, seconds: float = 0.3) -> float:
     out = C.c_double(0.0)
     _check(lib.qtet_fp64_peak(device, seconds, C.byref(out)), "qtet_fp64_peak")
     return out.value
+
+
+def fp64_peaks_tflops(device: int = 0, seconds: float = 0.5) -> dict:
+    """{'dfma': ..., 'dmma': ...}: both FP64 paths measured on the device (the roofline uses the higher one)."""
+    _torch()
+    a, b = C.c_double(0.0), C.c_double(0.0)
+    _check(lib.qtet_fp64_peak2(device, seconds, C.byref(a), C.byref(b)), "qtet_fp64_peak2")
+    return {"dfma": a.value, "dmma": b.value}
 
 
 class Problem:
@@ -150,6 +161,10 @@ class Problem:
                                          out.ctypes.data_as(C.POINTER(C.c_double))), "qtet_hamiltonian_host")
         return out
 
+    def reserve(self, batch: int):
+        """Size the workspaces for batches of up to `batch` points now (no allocation / synchronisation in later calls)."""
+        _check(lib.qtet_problem_reserve(self._h, int(batch)), "qtet_problem_reserve")
+
     def set_path(self, path: int):
         _check(lib.qtet_set_path(self._h, int(path)), "qtet_set_path")
 
@@ -165,6 +180,12 @@ class Problem:
         ms = (C.c_double * 3)(); n = (C.c_int64 * 3)(); pts = (C.c_int64 * 3)()
         _check(lib.qtet_profile_read(self._h, ms, n, pts), "qtet_profile_read")
         return {k: (ms[i], int(n[i]), int(pts[i])) for i, k in enumerate(("ql_scalar", "apply", "generic_or_householder"))}
+
+    def stats(self, reset: bool = False) -> dict:
+        """Cumulative health counters of this handle's kernels (see qtet_stats in include/qtet.h)."""
+        out = (C.c_int64 * 4)()
+        _check(lib.qtet_stats(self._h, out, 1 if reset else 0), "qtet_stats")
+        return {"direct_fallback": int(out[0]), "stream_overflow": int(out[1]), "nonconverged": int(out[2])}
 
     # ---- the hot path --------------------------------------------------------------------
     def _site(self, site) -> int:

@@ -55,6 +55,35 @@ def global_argmin(local_rows: np.ndarray, lo: int, loss_col: int):
     return int(best[1]), best[2:].copy()
 
 
+def global_argmin_device(problem, best_vars, best_loss, lo: int):
+    """Device-side form of `global_argmin` for large shards: the shard's arg-min is taken by the library's own reduction
+    kernel (qtet_argmin; first minimum wins, like np.argmin), only ONE (f+2)-double record per rank leaves the GPU -- through
+    the all_gather (NCCL over NVLink) -- instead of the whole [G/ws, f+1] result array (solver_mp.py:182-184).
+    best_vars [n, f], best_loss [n]: CUDA tensors of this rank's shard.  Returns (global_index, row[f+1])."""
+    import torch
+    import torch.distributed as dist
+    rank, ws = world()
+    f = best_vars.shape[1]
+    dev = best_loss.device
+    rec = torch.empty(f + 2, dtype=torch.float64, device=dev)
+    if best_loss.numel() > 0:
+        mn, ix = problem.argmin(best_loss)
+        rec[0:1] = mn
+        rec[1:2] = ix.to(torch.float64) + float(lo)
+        rec[2:] = best_vars.index_select(0, ix)[0]
+    else:
+        rec[0] = float('inf'); rec[1] = float(2 ** 52); rec[2:] = 0.0
+    if ws > 1:
+        gathered = [torch.empty_like(rec) for _ in range(ws)]
+        dist.all_gather(gathered, rec)
+        table = torch.stack(gathered).cpu().numpy()
+    else:
+        table = rec.cpu().numpy()[None, :]
+    order = np.lexsort((table[:, 1], table[:, 0]))          # by loss, then by global index
+    best = table[order[0]]
+    return int(best[1]), np.concatenate([best[2:], best[0:1]])
+
+
 def gather_rows(local_rows: np.ndarray, n_total: int, lo: int):
     """All-gather variable-length shards of rows into the full [n_total, width] array (used only when the
     caller asks for every guess' result, e.g. write_data; the solver itself needs just the arg-min)."""

@@ -85,12 +85,24 @@ def solver_mp(trainable_vars_limits: dict, const: dict, grid=solver_params['Npoi
         t2 = time.time()
         lo, hi = parallel.shard_bounds(G, rank, ws)
         mine = np.asarray(combos, dtype=np.float64).reshape(G, -1)[lo:hi]
-        if hi > lo:
-            rows = mp_opt_batch(mine, data_path2, const, target_site, epochs, lr, beta_1, amsgrad, write_data,
-                                train_sites, first_index=lo, problem=problem, quiet=(G > 64))
+        if G > 4096 and not write_data:
+            # large runs: nothing but the arg-min record leaves the GPU (device reduction + one all_gather)
+            import torch
+            if hi > lo:
+                bv, bl = mp_opt_batch(mine, data_path2, const, target_site, epochs, lr, beta_1, amsgrad, write_data,
+                                      train_sites, first_index=lo, problem=problem, quiet=True, on_device=True)
+            else:
+                dev = torch.device('cuda', problem.device)
+                bv = torch.zeros(0, sites, dtype=torch.float64, device=dev)
+                bl = torch.zeros(0, dtype=torch.float64, device=dev)
+            _, best_row = parallel.global_argmin_device(problem, bv, bl, lo)
         else:
-            rows = np.zeros((0, sites + 1))
-        _, best_row = parallel.global_argmin(rows, lo, sites)              # solver_mp.py:182-184
+            if hi > lo:
+                rows = mp_opt_batch(mine, data_path2, const, target_site, epochs, lr, beta_1, amsgrad, write_data,
+                                    train_sites, first_index=lo, problem=problem, quiet=(G > 64))
+            else:
+                rows = np.zeros((0, sites + 1))
+            _, best_row = parallel.global_argmin(rows, lo, sites)          # solver_mp.py:182-184
         dt = time.time() - t2
         optimal_vars = [float(best_row[i]) for i in range(sites)]
         min_loss = float(best_row[sites])

@@ -14,7 +14,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import make_const
+from conftest import make_const, record_ties
 
 pytestmark = pytest.mark.gpu
 
@@ -51,6 +51,7 @@ def _compare(native, O, const, X, site, path=None, loss_atol=None, grad_rtol=Non
         tr = O.trace(const, X[~same_t], site)
         idx = np.arange(tr.shape[0])
         assert np.abs(tr[idx, ts[~same_t]] - tr[idx, kr[~same_t]]).max() <= la
+    record_ties(f"N={N} f={const['sites']} site={site}", int((~same_t).sum()), len(X))
     gscale = np.maximum(1.0, np.abs(gr).max(axis=1, keepdims=True))
     err = (np.abs(grad - gr) / gscale)[same_t]
     emax = err.max() if err.size else 0.0          # every point a numerical tie (e.g. no hopping): nothing to compare

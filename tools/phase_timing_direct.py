@@ -32,8 +32,8 @@ _native.lib.qtet_debug_phase_cycles_direct(out, 1)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); prob.loss_grad(x); e1.record(); torch.cuda.synchronize()
 _native.lib.qtet_debug_phase_cycles_direct(out, 0)
-names = ["0 diag + recurrences", "1 sort/readback + c/phase setup", "2 evolution+loss", "3 S pairs", "4 G = row S row", "5 grad reduce+store",
-         "6 f=w^k powering", "7 psi(t*)", "8 a reduction", "9 records"]
+names = ["0 recurrences pass 2 (join, scale)", "1 sort/readback + c/phase setup", "2 evolution+loss", "3 S pairs", "4 G = row S row", "5 grad reduce+store",
+         "6 f=w^k powering", "7 psi(t*)", "8 a reduction", "9 records", "10 chi/ev loads + diagonal", "11 recurrence from the bottom", "12 recurrence from the top (join row)"]
 tot = sum(out[i] for i in range(len(names)))
 print(f"B={B} N={N} total step {e0.elapsed_time(e1):.3f} ms ; warp-cycles per point (4 points per warp):")
 for i, n in enumerate(names):
