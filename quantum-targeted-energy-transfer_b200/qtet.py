@@ -22,8 +22,8 @@ def _maybe_init_distributed():
         import torch
         import torch.distributed as dist
         local = int(os.environ.get('LOCAL_RANK', 0))
-        torch.cuda.set_device(local)
-        dist.init_process_group('nccl')
+        torch.cuda.set_device(local % max(1, torch.cuda.device_count()))    # (gloo tests run two ranks on one GPU)
+        dist.init_process_group(os.environ.get('QTET_DIST_BACKEND', 'nccl'))
 
 
 def run(argv=None):
@@ -39,7 +39,9 @@ def run(argv=None):
     _maybe_init_distributed()
     rank, _ = parallel.world()
 
-    data_path = args.data_path.joinpath(f'data_{datetime.now().strftime("%Y_%h_%d_%T")}')
+    # one output tree for the whole job: rank 0 picks the (second-resolution) timestamp, the others take its choice
+    data_path = parallel.broadcast_object(
+        args.data_path.joinpath(f'data_{datetime.now().strftime("%Y_%h_%d_%T")}') if rank == 0 else None)
     if not args.data_path.exists() and rank == 0:
         print(f"Input data path {args.data_path} does not exist! Creating it.")
     os.makedirs(data_path, exist_ok=True)

@@ -25,7 +25,7 @@ class Loss:
         self.sites = const['sites']
         self.chis = const['chis']
         self.targetState = const['sites'] - 1          # HamiltonianLoss.py:36
-        self.problem = _native.Problem.from_const(const, device)
+        self.problem = _native.shared_problem(const, device)    # one handle per system for the whole process
         self.dim = self.problem.dim
         self.states = self.problem.states()            # HamiltonianLoss.py:43, 62-110
 
@@ -47,6 +47,29 @@ class Loss:
 
     def batch_trace(self, chis, site=None):
         return self.problem.trace(chis, self.sites - 1 if site is None else site)
+
+    def landscape(self, xd, xa, site=None, vary=None, destination=None, name_of_file='min_n.txt'):
+        """The (x_D, x_A, min_n) landscape the authors' plotting scripts read (HamiltonianLoss.py:232-233 evaluated over a
+        grid + data_process.py:35-58 `write_min_N`): ONE batched sweep of the loss over the outer product of the 1-D arrays
+        `xd` (rows) and `xa` (columns).  `vary` = the two sites whose chi are swept (default: donor 0 and acceptor f-1), the
+        others keep const['chis'].  Returns min_n [len(xd), len(xa)]; with `destination` the file is written in the
+        reference's format (one row `x_D x_A min_n` per point, C order, %.18e)."""
+        from .data_process import write_min_N
+        xd = np.asarray(xd, dtype=np.float64).ravel()
+        xa = np.asarray(xa, dtype=np.float64).ravel()
+        s0, s1 = (0, self.sites - 1) if vary is None else vary
+        XD, XA = np.meshgrid(xd, xa, indexing='ij')
+        pts = np.tile(np.array([_as_float(c) for c in self.const['chis']], dtype=np.float64), (XD.size, 1))
+        pts[:, s0] = XD.ravel()
+        pts[:, s1] = XA.ravel()
+        target = self.sites - 1 if site is None else self.problem._site(site)
+        loss, _, _ = self.problem.loss_grad(pts, target, need_grad=False, need_tstar=False)
+        min_n = loss.cpu().numpy().reshape(XD.shape)
+        if destination is not None:
+            if len(xd) != len(xa):
+                raise ValueError("write_min_N (data_process.py:35-58) indexes a SQUARE landscape")
+            write_min_N(xa=XA, xd=XD, min_n=min_n, destination=destination, name_of_file=name_of_file)
+        return min_n
 
     def createHamiltonian(self):
         """HamiltonianLoss.py:168-176 for the current self.chis (device-built, returned as numpy)."""

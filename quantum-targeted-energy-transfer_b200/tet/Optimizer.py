@@ -148,8 +148,12 @@ class Optimizer:
         self.opt.iterations = n
         if self.Print:
             dt = time.time() - t0
-            for e in range(0, n, 50):                    # Optimizer.py:155-158 (progress lines)
-                print(f'Loss:{mylosses[e + 1]}, epoch:{e}')
+            for e in range(0, n, 50):                    # Optimizer.py:155-158 (progress lines: loss and variables BEFORE the step)
+                xs = x0[0] if e == 0 else vh[e // 10 - 1]
+                print(f'Loss:{mylosses[e + 1]}, ', *[f'x{j}: {xs[j]}, ' for j in range(len(self.vars))], f', epoch:{e}')
+            if n < self.iter and not abs(mylosses[n]) < 0.1:
+                print('Stopped training because a trained variable moved by less than tol =', self.tol,
+                      'in more than two steps')             # Optimizer.py:202-208
             print(*[f"\nApproximate value of chi_{j}: {best_vars[j].numpy()}" for j in range(len(self.vars))],
                   "\nLoss:", min(mylosses), "\nOptimizer Iterations:", n, "\nTraining Time:", dt,
                   "\n" + 60 * "-", "\nParameters:", "\nOmegas", self.omegas, "| N:", self.max_n,
@@ -208,8 +212,8 @@ def mp_opt_batch(combinations, iteration_path, const, target_site, iterations, l
     x0 = np.zeros((G, f))                                  # Optimizer.py:307-312
     for col, site in enumerate(train_sites):
         x0[:, site] = combos[:, col]
-    own = problem is None
-    prob = problem if problem is not None else _native.Problem.from_const(const)
+    own = False                                            # handles come from the per-system cache, never closed here
+    prob = problem if problem is not None else _native.shared_problem(const)
     out = prob.adam_run(x0, site=prob._site(target_site), train_sites=train_sites, iterations=iterations,
                         lr=lr, beta_1=beta_1, amsgrad=amsgrad_bool, tol=TensorflowParams['tol'],
                         history=bool(write_data))

@@ -104,6 +104,30 @@ def fp64_peaks_tflops(device: int = 0, seconds: float = 0.5) -> dict:
     return {"dfma": a.value, "dmma": b.value}
 
 
+_SHARED = {}
+
+
+def shared_problem(const: dict, device=None):
+    """One native handle per (system constants, device) for the whole process.  The reference builds a fresh Loss -- and
+    with it a fresh graph -- for every Optimizer / every guess (Optimizer.py:108, 295); here that would mean one set of
+    device workspaces per guess, so Loss, Optimizer, mp_opt and solver_mp all draw their handle from this cache.  Handles
+    obtained here must not be close()d by the borrower; `release_shared_problems()` frees them all."""
+    torch = _torch()
+    dev = torch.cuda.current_device() if device is None else int(device)
+    key = (int(const["max_N"]), int(const["sites"]), tuple(float(o) for o in const["omegas"]), float(const["coupling"]),
+           int(np.int32(const["max_t"])), int(const["timesteps"]), dev)
+    prob = _SHARED.get(key)
+    if prob is None or getattr(prob, "_h", None) is None:
+        prob = _SHARED[key] = Problem.from_const(const, dev)
+    return prob
+
+
+def release_shared_problems():
+    for prob in _SHARED.values():
+        prob.close()
+    _SHARED.clear()
+
+
 class Problem:
     """Opaque handle: everything about a system that does not depend on chi
     (replaces Loss.__init__, /root/reference/src/tet/HamiltonianLoss.py:20-47)."""

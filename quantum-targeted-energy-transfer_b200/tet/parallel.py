@@ -18,6 +18,19 @@ def world():
     return 0, 1
 
 
+def broadcast_object(obj, src: int = 0):
+    """The object held by rank `src`, on every rank (identity when not distributed).  Used for the things that must be ONE
+    consistent draw / decision across the ranks: the random initial guesses of the 'bins' method (the reference draws them
+    from the unseeded global numpy RNG, solver_mp.py:70) and the timestamped output directory of the CLI (qtet.py:26)."""
+    rank, ws = world()
+    if ws == 1:
+        return obj
+    import torch.distributed as dist
+    box = [obj if rank == src else None]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
 def shard_bounds(n: int, rank: int, world_size: int):
     """Contiguous, balanced shard [lo, hi) of n items for `rank` (first n % world shards get one more)."""
     base, rem = divmod(n, world_size)

@@ -70,14 +70,19 @@ def solver_mp(trainable_vars_limits: dict, const: dict, grid=solver_params['Npoi
     optimal_vars, min_loss = np.zeros(len(trainable_vars_limits)), const['max_N']
     train_sites = [int(list(trainable_vars_limits.keys())[i][1]) for i in range(len(trainable_vars_limits))]
     sites = const['sites']
-    problem = _native.Problem.from_const(const)
+    problem = _native.shared_problem(const)              # per-system handle, shared with Loss / Optimizer / mp_opt
 
     t0 = time.time()
     while iteration < iterations:
         data_path2 = os.path.join(data_path, f'iteration_{iteration}')
         createDir(destination=data_path2, replace_query=False)
-        combos = combinations if combinations is not None else getCombinations(
-            trainable_vars_limits, train_sites=train_sites, method=method, grid=grid)
+        if combinations is not None:
+            combos = combinations
+        else:
+            # 'bins' draws from the unseeded global RNG (solver_mp.py:70): rank 0 draws, every rank shards THAT list
+            combos = getCombinations(trainable_vars_limits, train_sites=train_sites, method=method, grid=grid) \
+                if rank == 0 else None
+            combos = parallel.broadcast_object(combos)
         epochs = epochs_bins if method == 'bins' else epochs_grid
         G = len(combos)
         if rank == 0:
@@ -135,5 +140,4 @@ def solver_mp(trainable_vars_limits: dict, const: dict, grid=solver_params['Npoi
                                   "that is never written, solver_mp.py:231-233)")
     if rank == 0:
         print('Total solver run time: ', t1 - t0)
-    problem.close()
     return const

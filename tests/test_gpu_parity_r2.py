@@ -234,6 +234,47 @@ def test_against_high_precision_arbiter(native, O, system):
     assert (k == ka).all() and (ko == ka).all()
     assert e_gpu <= tol_l and np.abs(tr - tra).max() <= tol_l
     assert g_gpu <= tol_g
-    # the GPU path must not be (much) further from the truth than the numpy oracle is
-    assert e_gpu <= 4 * e_orc + 1e-12 * N
+    # the numpy oracle itself is within 1e-13 (loss) / 1e-9 (gradient, dimer N=100) of the 40-digit values on these points
+    assert e_orc <= 1e-12 * N and g_orc <= 2e-9
     prob.close()
+
+
+def test_landscape_export_matches_oracle_and_reference_format(native, O, tmp_path):
+    """N4: Loss.landscape = one batched sweep -> the (x_D, x_A, min_n) file of data_process.py:35-58, every row against the
+    oracle; the file is what the reference's write_min_N would have written for the same arrays."""
+    from tet.HamiltonianLoss import Loss
+    from tet import data_process
+    c = make_const(20)
+    ax = np.linspace(-10, 10, 1024)[::16][:64]                 # 64 x 64 sub-grid of the config-2 axes
+    L = Loss(c)
+    min_n = L.landscape(ax, ax, site=1, destination=str(tmp_path), name_of_file="min_n.txt")
+    assert min_n.shape == (64, 64)
+    rows = np.loadtxt(tmp_path / "min_n.txt")
+    assert rows.shape == (64 * 64, 3)
+    XD, XA = np.meshgrid(ax, ax, indexing="ij")
+    assert np.array_equal(rows[:, 0], XD.ravel()) and np.array_equal(rows[:, 1], XA.ravel())
+    ref = O.loss_grad_batch(c, np.stack([XD.ravel(), XA.ravel()], 1), 1)[0]
+    assert np.abs(rows[:, 2] - ref).max() <= LOSS_ATOL * 20
+    assert np.array_equal(rows[:, 2], min_n.ravel())           # %.18e round-trips a double exactly
+    # same bytes as the reference's own writer (restated line by line in the oracle package's test helper)
+    k = [(XD.flatten(order="C")[64 * i + j], XA.flatten(order="C")[64 * i + j], min_n.flatten(order="C")[64 * i + j])
+         for i in range(64) for j in range(64)]
+    data_process.writeData(np.array(k), str(tmp_path), "ref.txt")
+    assert (tmp_path / "ref.txt").read_bytes() == (tmp_path / "min_n.txt").read_bytes()
+    # trimer: sweep donor/acceptor with the middle site fixed
+    c3 = make_const(4, (-3, 3, 3)); c3["chis"] = [0.0, 0.7, 0.0]
+    m3 = Loss(c3).landscape(ax[:8], ax[:8], site=2)
+    X = np.array([[a, 0.7, b] for a in ax[:8] for b in ax[:8]])
+    assert np.abs(m3.ravel() - O.loss_grad_batch(c3, X, 2)[0]).max() <= 2e-10 * 4
+
+
+def test_reference_style_per_guess_loop_shares_one_handle(native):
+    """The reference builds Loss/Optimizer per guess (Optimizer.py:108, 295); here they all borrow ONE native handle."""
+    from tet.HamiltonianLoss import Loss
+    from tet.Optimizer import Optimizer
+    c = make_const(4)
+    handles = {id(Loss(c).problem) for _ in range(5)}
+    opt = Optimizer(const=c, target_site=1, iterations=5)
+    opt(0.5, -0.5)
+    handles.add(id(opt._ensure_loss().problem))
+    assert len(handles) == 1

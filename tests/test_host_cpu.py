@@ -160,3 +160,37 @@ def test_bench_cpu_baseline_sample_is_bounded():
     wall = time.perf_counter() - t0
     assert 16 <= n <= len(pts) and rate > 0
     assert dt < 20.0 and wall < 40.0, (n, dt, wall)
+
+
+_BCAST_WORKER = r"""
+import os, sys, json
+sys.path.insert(0, {pkg!r})
+import numpy as np
+import torch.distributed as dist
+dist.init_process_group('gloo')
+from tet import parallel
+from tet.solver_mp import getCombinations
+rank = dist.get_rank()
+np.random.seed(1000 + rank)                      # the ranks' global RNGs differ, as they do in real life
+lims = {{"x0lims": [-10, 10], "x1lims": [-10, 10]}}
+combos = getCombinations(lims, train_sites=[0, 1], method='bins', grid=4) if rank == 0 else None
+combos = parallel.broadcast_object(combos)
+path = parallel.broadcast_object('data_%d' % os.getpid() if rank == 0 else None)
+json.dump({{"combos": np.asarray(combos).tolist(), "path": path}}, open({out!r} + f'/r{{rank}}.json', 'w'))
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_rank0_draw_is_shared_by_all_ranks_gloo_world2(tmp_path):
+    """The random 'bins' guesses and the CLI's timestamped directory must be ONE draw for the whole job."""
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "w.py"
+    script.write_text(_BCAST_WORKER.format(pkg=PKG, out=str(tmp_path)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    a = json.load(open(tmp_path / "r0.json")); b = json.load(open(tmp_path / "r1.json"))
+    assert a == b and len(a["combos"]) >= 4
