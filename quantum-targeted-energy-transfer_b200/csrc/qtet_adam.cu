@@ -295,7 +295,7 @@ extern "C" int qtet_adam_run(qtet_problem* p, double* chis_dev, int64_t B, int t
     // The loss+grad kernels of the direct path read the number of live guesses from device memory, so the epoch loop
     // never waits for the GPU: the host only keeps an UPPER BOUND of the live count (it can only fall) to size the grids,
     // refreshed from a pinned word that trails the device by kLag epochs, and stops once that word reads zero.
-    const bool devcount = (p->path == QTET_PATH_DIRECT) && B <= (1LL << 22) && !std::getenv("QTET_ADAM_SYNC");
+    const bool devcount = (p->path == QTET_PATH_DIRECT) && direct_eligible(p->view) && B <= (1LL << 22) && !std::getenv("QTET_ADAM_SYNC");
     int epoch = 0, executed = -1;
     if (devcount) {
         constexpr int kLag = 4;

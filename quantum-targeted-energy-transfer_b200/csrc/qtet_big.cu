@@ -289,6 +289,111 @@ __global__ void __launch_bounds__(kWarpsBig * 32) ql_scalar_big_kernel(BigQlArgs
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Direct path: eigenvalues only (one sweep family, full precision), sorted ascending, plus the shifted diagonal the
+// eigenvector kernel starts its recurrences from.  No rotation stream: 16 d bytes per point leave this kernel instead of
+// ~(d^2 + 8 d) * 16.
+// ------------------------------------------------------------------------------------------------
+template <bool LOCAL>
+__global__ void __launch_bounds__(kWarpsBig * 32) eig_scalar_big_kernel(BigQlArgs a) {
+    extern __shared__ double sm[];
+    const ProblemView& pv = a.pv;
+    const int d = pv.d, f = pv.f;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    QlLaneBig<LOCAL> t;
+    t.arr = LOCAL ? nullptr : sm + (size_t)warp * 2 * d * 32 + lane;
+    t.d = d;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.overflow_count = 0;      // the eigenvector kernel (stream-ordered after us) appends
+    const long long nbatch = (a.n + 31) / 32;
+    for (long long batch = (long long)blockIdx.x * kWarpsBig + warp; batch < nbatch; batch += (long long)gridDim.x * kWarpsBig) {
+        const long long p = batch * 32 + lane;
+        const bool valid = p < a.n;
+        const long long pc = valid ? p : a.n - 1;
+        double hchi[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hchi[k] = (k < f && !a.use_tri) ? 0.5 * a.chis[pc * f + k] : 0.0;
+        double sum = 0.0;
+        for (int m = 0; m < d; ++m) {
+            double acc, off;
+            if (a.use_tri) {
+                acc = a.bs.tri_d[pc * d + m];
+                off = (m < d - 1) ? a.bs.tri_e[pc * d + m] : 0.0;
+            } else {
+                acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (k < f) {
+                        const double n = pv.occ[m * f + k];
+                        acc = acc + (pv.omegas[k] * n + hchi[k] * (n * n));
+                    }
+                }
+                off = (m < d - 1) ? pv.offd[m] : 0.0;
+            }
+            t.dg(m) = acc;
+            t.of(m) = off;
+            sum += acc;
+        }
+        const double mean = sum / (double)d;
+        for (int m = 0; m < d; ++m) {
+            const double x = t.dg(m) - mean;
+            t.dg(m) = x;
+            if (valid) a.bs.adiag[p * d + m] = x;         // what the recurrences of the eigenvector kernel run on
+        }
+        Mask128 small = t.scan_small();
+        int l = 0, iter = 0;
+        bool failed = false;
+        while (true) {
+            const int lnew = small.first_clear_ge(l, d - 1);
+            if (lnew < 0) break;
+            if (lnew != l) iter = 0;
+            l = lnew;
+            const int m = small.first_set_ge(l);
+            if (++iter > 60) { failed = true; break; }
+            double g = t.wilkinson_g(l, m);
+            double s = 1.0, c = 1.0, pp = 0.0, dnext = 0.0;
+            bool broke = false;
+            double d_hi = t.dg(m), d_i = t.dg(m - 1), e_i = t.of(m - 1);
+            WalkBit fb; fb.at(m);
+            for (int i = m - 1; i >= l; --i) {
+                const int in = (i > l) ? i - 1 : i;
+                const double d_n = t.dg(in), e_n = t.of(in);
+                const double fo = s * e_i, bo = c * e_i;
+                const double r2 = fma(fo, fo, g * g);
+                if (r2 < kTinyR2) { t.of(i + 1) = 0.0; t.dg(i + 1) = d_hi - pp; t.of(m) = 0.0; broke = true; break; }
+                const double rinv = rsqrt_fast(r2);
+                const double r = r2 * rinv;
+                s = fo * rinv; c = g * rinv;
+                g = d_hi - pp;
+                const double rr = fma(d_i - g, s, 2.0 * c * bo);
+                pp = s * rr;
+                const double dnew = g + pp;
+                t.dg(i + 1) = dnew;
+                g = fma(c, rr, -bo);
+                t.of(i + 1) = r;                           // of(m) is reset below
+                put_bit(small, fb, r <= kEps * (fabs(dnew) + fabs(dnext)));
+                fb.down();
+                dnext = dnew; d_hi = d_i; d_i = d_n; e_i = e_n;
+            }
+            if (broke) { small = t.scan_small(); continue; }
+            const double dlnew = d_hi - pp;
+            t.dg(l) = dlnew; t.of(l) = g; t.of(m) = 0.0;
+            small.set(m);
+            small.put(l, fabs(g) <= kEps * (fabs(dlnew) + fabs(dnext)));
+        }
+        for (int i = 1; i < d; ++i) {                      // ascending order (insertion sort; the QL output is close to sorted)
+            const double x = t.dg(i);
+            int j = i - 1;
+            while (j >= 0 && t.dg(j) > x) { t.dg(j + 1) = t.dg(j); --j; }
+            t.dg(j + 1) = x;
+        }
+        if (valid) {
+            if (failed) t.dg(0) = __longlong_as_double(0x7ff8000000000000LL);      // poisons the point: it takes the fallback
+            for (int m = 0; m < d; ++m) a.bs.ev[p * d + m] = t.dg(m);
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace
 
 struct BigWorkspace {
@@ -301,6 +406,12 @@ struct BigWorkspace {
     bool ql_local = false;                // scalar QL keeps the tridiagonal in local memory (more resident warps)
     int ql_ctas = 8;                      // ... CTAs of kWarpsBig warps per SM in that mode
     size_t budget = 0;                    // bytes the workspace may take (from the free HBM, queried when it has to grow)
+    // direct path: two chunk buffers, the Householder + eigenvalue kernels of chunk c+1 run on `aux` beside the eigenvector /
+    // evolution / gradient kernel of chunk c
+    bool direct = false;
+    int* fb_count = nullptr;              // [2]
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr};
 };
 
 bool big_eligible(const ProblemView& pv) {
@@ -314,6 +425,13 @@ void big_workspace_free(BigWorkspace* ws) {
     if (ws->blob) cudaFree(ws->blob);
     if (ws->overflow_count) cudaFree(ws->overflow_count);
     if (ws->pair_tab) cudaFree(ws->pair_tab);
+    if (ws->fb_count) cudaFree(ws->fb_count);
+    if (ws->aux) cudaStreamDestroy(ws->aux);
+    if (ws->ev_fork) cudaEventDestroy(ws->ev_fork);
+    for (int i = 0; i < 2; ++i) {
+        if (ws->ev_a[i]) cudaEventDestroy(ws->ev_a[i]);
+        if (ws->ev_b[i]) cudaEventDestroy(ws->ev_b[i]);
+    }
     delete ws;
 }
 
@@ -326,6 +444,7 @@ int launch_big(const ProblemView& pv, BigWorkspace** wsp, const double* chis, in
     if (!big_eligible(pv)) { set_error("large-d split path not eligible for this problem"); return QTET_EUNSUPPORTED; }
     BigWorkspace* ws = *wsp;
     const int d = pv.d;
+    if (ws && ws->direct) { cudaDeviceSynchronize(); big_workspace_free(ws); ws = nullptr; *wsp = nullptr; }     // path switched: rebuild
     if (!ws) {
         ws = new BigWorkspace();
         *wsp = ws;
@@ -458,6 +577,151 @@ int launch_big(const ProblemView& pv, BigWorkspace** wsp, const double* chis, in
         if (rc) return rc;
         rc = launch_generic_list(pv, cchis, overflow_list, ws->overflow_count, n, site, closs, cgrad, cts, ctrace, st);
         if (rc) return rc;
+    }
+    return QTET_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Direct large-d path: [Householder] -> eigenvalues (scalar QL, no stream) -> eigenvectors by recurrences [+ V = Q Z] ->
+// evolution -> gradient.  Chunks are double-buffered: the Householder and eigenvalue kernels of chunk c+1 run on an auxiliary
+// stream while the eigenvector / evolution / gradient kernel of chunk c runs on the caller's stream.
+// ------------------------------------------------------------------------------------------------
+bool big_direct_eligible(const ProblemView& pv) {
+    if (!big_eligible(pv)) return false;
+    if (std::getenv("QTET_BIG_SMEM") || pv.T > bigreg_max_timesteps()) return false;
+    const int D = bigreg_padded_dim(pv.d);
+    if (D == 0 || D > bigreg_direct_max_dim(!pv.tridiag)) return false;
+    if (pv.tridiag && !pv.offd_nonzero) return false;
+    return true;
+}
+
+static long long big_direct_chunk(const ProblemView& pv, long long B) {
+    const bool dense = !pv.tridiag;
+    const size_t per_point = (size_t)pv.d * 8 * (dense ? 4 : 2) + 4 + (dense ? (size_t)pv.d * pv.d * 8 : 0);
+    long long chunk = ((B + 3) / 4 + 31) / 32 * 32;                 // four chunks per call
+    const long long lo = dense ? 16384 : 65536;
+    if (chunk < lo) chunk = lo;
+    long long cap = (long long)(((size_t)4 << 30) / per_point) / 32 * 32;     // <= 4 GiB per buffer
+    if (const char* env = std::getenv("QTET_BIG_WS_GIB")) { const double g = std::atof(env); if (g > 0) cap = (long long)(g * 0.5 * 1073741824.0 / (double)per_point) / 32 * 32; }
+    if (cap < 32) cap = 32;
+    if (chunk > cap) chunk = cap;
+    const long long all = (B + 31) / 32 * 32;
+    if (chunk > all) chunk = all;
+    return chunk;
+}
+
+int launch_big_direct(const ProblemView& pv, BigWorkspace** wsp, const double* chis, int64_t B, int site, double* loss,
+                      double* grad, int32_t* tstar, double* trace, cudaStream_t st, Profiler* prof, const ChunkHook* hook) {
+    if (B <= 0) return QTET_OK;
+    if (!big_direct_eligible(pv)) { set_error("large-d direct path not eligible for this problem"); return QTET_EUNSUPPORTED; }
+    BigWorkspace* ws = *wsp;
+    const int d = pv.d;
+    const bool dense = !pv.tridiag;
+    if (ws && !ws->direct) { cudaDeviceSynchronize(); big_workspace_free(ws); ws = nullptr; *wsp = nullptr; }   // path switched: rebuild
+    if (!ws) {
+        ws = new BigWorkspace();
+        *wsp = ws;
+        ws->direct = true;
+        QTET_CUDA(cudaGetDevice(&ws->device));
+        QTET_CUDA(cudaDeviceGetAttribute(&ws->sms, cudaDevAttrMultiProcessorCount, ws->device));
+        ws->regD = bigreg_padded_dim(d);
+        ws->maxr = 4;                                     // no round headers: the replay region of the kernel stays empty
+        ws->ql_local = true; ws->ql_ctas = 16;
+        if (const char* env = std::getenv("QTET_QL_LOCAL")) { ws->ql_local = std::atoi(env) > 0; if (std::atoi(env) > 1) ws->ql_ctas = std::atoi(env); }
+        std::vector<unsigned short> tab;
+        for (int i = 0; i < ws->regD; ++i)
+            for (int j = i + 1; j < ws->regD; ++j) tab.push_back((unsigned short)(i | (j << 8)));
+        if (tab.empty()) tab.push_back(0);
+        QTET_CUDA(cudaMalloc(&ws->pair_tab, tab.size() * sizeof(unsigned short)));
+        QTET_CUDA(cudaMemcpy(ws->pair_tab, tab.data(), tab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+        QTET_CUDA(cudaMalloc(&ws->fb_count, 2 * sizeof(int)));
+        QTET_CUDA(cudaStreamCreateWithFlags(&ws->aux, cudaStreamNonBlocking));
+        QTET_CUDA(cudaEventCreateWithFlags(&ws->ev_fork, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) {
+            QTET_CUDA(cudaEventCreateWithFlags(&ws->ev_a[i], cudaEventDisableTiming));
+            QTET_CUDA(cudaEventCreateWithFlags(&ws->ev_b[i], cudaEventDisableTiming));
+        }
+    }
+    const long long chunk = big_direct_chunk(pv, B);
+    auto align = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t o_ad = align((size_t)chunk * d * 8);
+    const size_t o_list = o_ad + align((size_t)chunk * d * 8);
+    const size_t o_trid = o_list + align((size_t)chunk * 4);
+    const size_t o_trie = o_trid + (dense ? align((size_t)chunk * d * 8) : 0);
+    const size_t o_q = o_trie + (dense ? align((size_t)chunk * d * 8) : 0);
+    const size_t buf_bytes = o_q + (dense ? align((size_t)chunk * d * d * 8) : 0);
+    if (2 * buf_bytes > ws->blob_bytes) {
+        if (ws->blob) { cudaDeviceSynchronize(); cudaFree(ws->blob); }
+        ws->blob = nullptr; ws->blob_bytes = 0;
+        if (cudaMalloc(&ws->blob, 2 * buf_bytes) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(large-d direct workspace) failed"); return QTET_ENOMEM; }
+        ws->blob_bytes = 2 * buf_bytes;
+    }
+    // eigenvalue kernel: shared-memory tridiagonal when the chunk has fewer batches than that variant has warp slots
+    const size_t smem_sh = (size_t)kWarpsBig * 2 * d * 32 * sizeof(double);
+    QTET_CUDA(cudaFuncSetAttribute(eig_scalar_big_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sh));
+    QTET_CUDA(cudaFuncSetAttribute(eig_scalar_big_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    int per_sm_sh = 0, per_sm_lo = 0;
+    QTET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_sh, eig_scalar_big_kernel<false>, kWarpsBig * 32, smem_sh));
+    QTET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_lo, eig_scalar_big_kernel<true>, kWarpsBig * 32, 0));
+    if (per_sm_sh < 1) per_sm_sh = 1;
+    if (per_sm_lo < 1) per_sm_lo = 1;
+    if (per_sm_lo > ws->ql_ctas) per_sm_lo = ws->ql_ctas;
+    const long long slots_sh = (long long)ws->sms * per_sm_sh * kWarpsBig;
+    const bool ql_local = ws->ql_local && chunk / 32 > slots_sh;
+    const size_t smemA = ql_local ? 0 : smem_sh;
+    auto eigk = ql_local ? eig_scalar_big_kernel<true> : eig_scalar_big_kernel<false>;
+    const int per_sm_a = ql_local ? per_sm_lo : per_sm_sh;
+
+    QTET_CUDA(cudaEventRecord(ws->ev_fork, st));
+    QTET_CUDA(cudaStreamWaitEvent(ws->aux, ws->ev_fork, 0));
+    int c = 0;
+    for (long long lo = 0; lo < B; lo += chunk, ++c) {
+        const int buf = c & 1;
+        char* base = ws->blob + (size_t)buf * buf_bytes;
+        const long long n = (B - lo < chunk) ? (B - lo) : chunk;
+        BigStream bs;
+        bs.ev = (double*)base; bs.adiag = (double*)(base + o_ad);
+        bs.capit = 0; bs.maxr = ws->maxr;
+        if (dense) { bs.tri_d = (double*)(base + o_trid); bs.tri_e = (double*)(base + o_trie); bs.qmat = (double*)(base + o_q); }
+        int* fb_list = (int*)(base + o_list);
+        int* fb_count = ws->fb_count + buf;
+        const double* cchis = chis + lo * pv.f;
+        double* closs = loss ? loss + lo : nullptr;
+        double* cgrad = grad ? grad + lo * pv.f : nullptr;
+        int32_t* cts = tstar ? tstar + lo : nullptr;
+        double* ctrace = trace ? trace + lo * pv.T : nullptr;
+        // aux: Householder + eigenvalues of chunk c, once the consumer of chunk c-2 has released this buffer
+        if (c >= 2) QTET_CUDA(cudaStreamWaitEvent(ws->aux, ws->ev_b[buf], 0));
+        if (hook && hook->before) { const int hrc = hook->before(hook->ctx, lo, n, ws->aux); if (hrc) return hrc; }
+        int rc;
+        if (dense) {
+            if (prof) prof->begin(2, n, ws->aux);
+            rc = launch_hh_reg(pv, cchis, n, bs, ws->sms, ws->aux);
+            if (prof) prof->finish(2, ws->aux);
+            if (rc) return rc;
+        }
+        BigQlArgs qa;
+        qa.pv = pv; qa.chis = cchis; qa.n = n; qa.bs = bs; qa.use_tri = dense ? 1 : 0;
+        qa.overflow_list = fb_list; qa.overflow_count = fb_count;
+        long long gridA = (long long)ws->sms * per_sm_a;
+        const long long needA = ((n + 31) / 32 + kWarpsBig - 1) / kWarpsBig;
+        if (gridA > needA) gridA = needA;
+        if (prof) prof->begin(0, n, ws->aux);
+        eigk<<<(unsigned)gridA, kWarpsBig * 32, smemA, ws->aux>>>(qa);
+        count_launch();
+        if (prof) prof->finish(0, ws->aux);
+        QTET_CUDA(cudaGetLastError());
+        QTET_CUDA(cudaEventRecord(ws->ev_a[buf], ws->aux));
+        // caller's stream: eigenvectors, evolution, gradient of chunk c
+        QTET_CUDA(cudaStreamWaitEvent(st, ws->ev_a[buf], 0));
+        if (prof) prof->begin(1, n, st);
+        rc = launch_replay_reg(pv, cchis, n, site, bs, ws->pair_tab, closs, cgrad, cts, ctrace, ws->sms, st, true, fb_list, fb_count);
+        if (prof) prof->finish(1, st);
+        if (rc) return rc;
+        rc = launch_generic_list(pv, cchis, fb_list, fb_count, n, site, closs, cgrad, cts, ctrace, st);
+        if (rc) return rc;
+        QTET_CUDA(cudaEventRecord(ws->ev_b[buf], st));
+        if (hook && hook->after) { const int hrc = hook->after(hook->ctx, lo, n, st); if (hrc) return hrc; }
     }
     return QTET_OK;
 }

@@ -17,6 +17,8 @@ struct BigStream {
     double* tri_d = nullptr;       // [n][d]
     double* tri_e = nullptr;       // [n][d]
     double* qmat = nullptr;        // [n][d][d]
+    // direct path (eigenvectors by two-sided recurrences): written by the eigenvalue-only QL kernel
+    double* adiag = nullptr;       // [n][d]           diagonal of the (Householder-reduced) tridiagonal minus its mean
 };
 
 // register-resident kernels (qtet_bigreg.cu); they store / expect Q column-major
@@ -25,7 +27,9 @@ int bigreg_max_timesteps();
 int launch_hh_reg(const ProblemView& pv, const double* chis, int64_t n, const BigStream& bs, int sms, cudaStream_t st);
 int launch_replay_reg(const ProblemView& pv, const double* chis, int64_t n, int site, const BigStream& bs,
                       const unsigned short* pair_tab, double* loss, double* grad, int32_t* tstar, double* trace, int sms,
-                      cudaStream_t st);
+                      cudaStream_t st, bool direct = false, int* fb_list = nullptr, int* fb_count = nullptr);
+// largest padded dimension for which the direct kernels exist (dense H: the V = Q Z tensor-core product must fit the registers)
+int bigreg_direct_max_dim(bool dense);
 
 int launch_generic_mode(const ProblemView& pv, const double* chis, int64_t B, int site, double* loss, double* grad,
                         int32_t* tstar, double* trace, cudaStream_t st, int mode, const BigStream& bs);

@@ -82,9 +82,11 @@ __device__ __forceinline__ double fast_rcp(double x) {
 
 #ifdef QTET_PHASE_TIMING
 __device__ unsigned long long g_big_phase_cycles[16];
-#define BPHASE_START() long long _t0 = clock64()
+#define BPHASE_DECL() long long _t0 = 0
+#define BPHASE_START() _t0 = clock64()
 #define BPHASE_MARK(idx) do { const long long _t = clock64(); if (tid == 0) atomicAdd(&g_big_phase_cycles[idx], (unsigned long long)(_t - _t0)); _t0 = _t; } while (0)
 #else
+#define BPHASE_DECL() do {} while (0)
 #define BPHASE_START() do {} while (0)
 #define BPHASE_MARK(idx) do {} while (0)
 #endif
@@ -97,6 +99,8 @@ struct RegArgs {
     BigStream bs;
     const unsigned short* pair_tab;   // [D(D-1)/2]  i | j << 8, lexicographic (i, j > i); used by the D <= 66 kernels
     double* loss; double* grad; int* tstar; double* trace;
+    int* fb_list = nullptr;           // direct variant: points handed to the fused generic kernel ...
+    int* fb_count = nullptr;          // ... and their count
 };
 
 // a[k] and a[k+1] of a register array for a CTA-uniform dynamic k: a jump table, not D predicated moves.
@@ -177,6 +181,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) hh_reg_kernel(RegArgs a_) {
     for (long long b = blockIdx.x; b < a_.n; b += gridDim.x) {
         const double* chi = a_.chis + b * f;
         __syncthreads();
+        BPHASE_DECL();
         BPHASE_START();
         // ---- my row of H: hopping part (symmetric, so column `row` read coalesced) + diagonal
         double a[D];
@@ -418,7 +423,103 @@ constexpr int reg_cap(int nw, int minb) {
     return r > 255 ? 255 : r;
 }
 
-template <int D, int NW, int MINB, int GS>
+// ------------------------------------------------------------------------------------------------
+// DIRECT variant: eigenvectors of the tridiagonal straight from its eigenvalues (no rotation stream, no replay).
+// Thread i runs the three-term recurrence of (T - lam_i) z = 0 from the bottom and from the top and joins the two at
+// the row r that maximises |p_r q_r| (see qtet_direct.cu).  At d ~ 100 the recurrences leave the FP64 range (growth up to
+// ||T|| / b per row), so the running pair is rescaled by 2^-256 whenever it exceeds 2^200; the rescale events of the
+// bottom-up pass are kept in a 128-bit mask, the top-down pass is deterministic and simply replays its own.
+// ------------------------------------------------------------------------------------------------
+constexpr double kGapGS = 2.44140625e-4;                // 2^-12: re-orthogonalise neighbours closer than this (x ||T||)
+constexpr double kGapFB = 5.820766091346741e-11;        // 2^-34: numerically degenerate -> generic kernel
+constexpr double kRecBig = 1.6069380442589903e60;       // 2^200
+constexpr double kRecF = 8.636168555094445e-78;         // 2^-256
+
+__device__ __forceinline__ double rsqrt_fast_d(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y * y, 1.0);
+    return fma(y * e, fma(e, 0.375, 0.5), y);
+}
+__device__ __forceinline__ double rec_scale(int m) {      // (2^-256)^m, 0 from m = 4 on (2^-1024 is not a double)
+    return m <= 0 ? 1.0 : (m == 1 ? kRecF : (m == 2 ? kRecF * kRecF : (m == 3 ? kRecF * kRecF * kRecF : 0.0)));
+}
+__device__ __forceinline__ int rec_key(double sp, double sq, int e) {      // ~ log2 |p q| of the TRUE (unscaled) values
+    const double pr = fabs(sp * sq);
+    return ((__double2hiint(pr) >> 20) & 0x7ff) + 256 * e;
+}
+
+// Column `i` of Z (eigenvector of the tridiagonal (sa, sb) for eigenvalue lam), normalised, into zc[k * ld], k < d.
+// Returns false when the recurrences produced something unusable (NaN / overflow): the point then takes the fallback.
+__device__ __forceinline__ bool direct_column(int d, double lam, const double* __restrict__ sa, const double* __restrict__ sb,
+                                              const double* __restrict__ sib, double* zc, int ld) {
+    unsigned long long qlo = 0ull, qhi = 0ull;           // bit k: the bottom-up pass rescaled at entry k (applies to entries <= k)
+    // from the bottom: q_{k-1} = ((lam - a_k) q_k - b_k q_{k+1}) / b_{k-1},  q_{d-1} = 1
+    {
+        double qn = 0.0, qc = 1.0;
+        zc[(size_t)(d - 1) * ld] = 1.0;
+#pragma unroll 4
+        for (int k = d - 1; k >= 1; --k) {
+            double val = fma(lam - sa[k], qc, -(sb[k] * qn)) * sib[k - 1];
+            qn = qc; qc = val;
+            if (fabs(qc) > kRecBig) {
+                qc *= kRecF; qn *= kRecF;
+                if (k - 1 < 64) qlo |= 1ull << (k - 1); else qhi |= 1ull << (k - 1 - 64);
+            }
+            zc[(size_t)(k - 1) * ld] = qc;
+        }
+    }
+    const int eq0 = __popcll(qlo) + __popcll(qhi);       // scale epoch of q_0
+    auto qbit = [&](int k) -> int { return (int)(((k < 64) ? (qlo >> k) : (qhi >> (k - 64))) & 1ull); };
+    // from the top: p_{k+1} = ((lam - a_k) p_k - b_{k-1} p_{k-1}) / b_k,  p_0 = 1; join row r = argmax |p_k q_k|
+    int r = 0, epr = 0, eqr = eq0;
+    double pr = 1.0, qr = zc[0];
+    {
+        double pm = 0.0, pc = 1.0;
+        int ep = 0, eq = eq0;
+        int best = rec_key(1.0, qr, eq0);
+#pragma unroll 4
+        for (int k = 0; k < d - 1; ++k) {
+            eq -= qbit(k);                                // epoch of q_{k+1}
+            const double bm = (k >= 1) ? sb[k - 1] : 0.0;
+            const double pn = fma(lam - sa[k], pc, -(bm * pm)) * sib[k];
+            pm = pc; pc = pn;
+            if (fabs(pc) > kRecBig) { pc *= kRecF; pm *= kRecF; ++ep; }
+            const double sq = zc[(size_t)(k + 1) * ld];
+            const int ky = rec_key(pc, sq, ep + eq);
+            if (ky > best) { best = ky; r = k + 1; pr = pc; qr = sq; epr = ep; eqr = eq; }
+        }
+    }
+    // second pass from the top: z_k = p_k / p_r above the join, q_k / q_r from the join down
+    const double invp = fast_rcp(pr), invq = fast_rcp(qr);
+    double ss = 0.0;
+    {
+        double pm = 0.0, pc = 1.0;
+        int ep = 0, eq = eq0;
+#pragma unroll 4
+        for (int k = 0; k < d; ++k) {
+            const bool above = k < r;
+            const double raw = above ? pc : zc[(size_t)k * ld];
+            const double x = raw * rec_scale(above ? (epr - ep) : (eqr - eq)) * (above ? invp : invq);
+            zc[(size_t)k * ld] = x;
+            ss = fma(x, x, ss);
+            if (k < d - 1) {
+                eq -= qbit(k);
+                const double bm = (k >= 1) ? sb[k - 1] : 0.0;
+                const double pn = fma(lam - sa[k], pc, -(bm * pm)) * sib[k];
+                pm = pc; pc = pn;
+                if (fabs(pc) > kRecBig) { pc *= kRecF; pm *= kRecF; ++ep; }
+            }
+        }
+    }
+    const bool ok = (ss >= 0.5 && ss < 1e300);           // z_r = 1: |z|^2 >= 1 unless NaN / overflow
+    const double rn = ok ? rsqrt_fast_d(ss) : 0.0;
+#pragma unroll 4
+    for (int k = 0; k < d; ++k) zc[(size_t)k * ld] *= rn;
+    return ok;
+}
+
+template <int D, int NW, int MINB, int GS, bool DIRECT = false>
 __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) replay_reg_kernel(RegArgs a) {
     using L = RpLayout<D, NW>;
     constexpr int NT = L::NT, DP = L::DP, LDV = L::LDV, NP = L::NP;
@@ -457,6 +558,127 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) replay
     const double dt = (T > 1) ? pv.tgrid[1] : 0.0;
 
     for (long long b = blockIdx.x; b < a.n; b += gridDim.x) {
+        BPHASE_DECL();
+        double v[D];
+        if constexpr (DIRECT) {
+            __syncthreads();                                 // previous point is done with every shared region
+            BPHASE_START();
+            constexpr int KP = L::KP;
+            double* zs = vsm;                                // [KP rows k][LDV]: column i = eigenvector i of the tridiagonal
+            double* sa = vec;                                // [DP] shifted diagonal   (vec is rewritten later)
+            double* sb = vec + DP;                           // [DP] b_k = T[k+1,k]
+            double* sib = vec + 2 * DP;                      // [DP] 1 / b_k
+            unsigned* gsm = reinterpret_cast<unsigned*>(ired + 4);      // [4] bit i: eigenvalue i is close to eigenvalue i-1
+            const double* adg = a.bs.adiag + (size_t)b * d;
+            const double* evp = a.bs.ev + (size_t)b * d;
+            if (tid < 8) ired[tid] = 0;
+            for (int k = tid; k < DP; k += NT) {
+                const double off = (k < d - 1) ? (dense ? a.bs.tri_e[(size_t)b * d + k] : pv.offd[k]) : 0.0;
+                sa[k] = (k < d) ? adg[k] : 0.0;
+                sb[k] = off;
+                sib[k] = (k < d - 1) ? 1.0 / off : 0.0;
+            }
+            // padding: rows d .. KP-1 (the V = Q Z product reads whole k tiles) and columns d .. LDV-1 hold zeros
+            for (int idx = tid; idx < (KP - d) * LDV; idx += NT) zs[(size_t)d * LDV + idx] = 0.0;
+            if (row >= d && row < LDV) {
+                for (int k = 0; k < d; ++k) zs[(size_t)k * LDV + row] = 0.0;
+            }
+            __syncthreads();
+            if (row < d) {
+                const double lam = evp[row];
+                const double nrm = fmax(fabs(evp[0]), fabs(evp[d - 1]));
+                bool fb = !direct_column(d, lam, sa, sb, sib, zs + row, LDV);
+                if (row >= 1) {
+                    const double gap = lam - evp[row - 1];
+                    if (!(gap > kGapFB * nrm)) fb = true;            // also catches NaN (the QL did not converge)
+                    else if (gap < kGapGS * nrm) atomicOr(&gsm[row >> 5], 1u << (row & 31));
+                }
+                if (fb) ired[2] = 1;
+            }
+            __syncthreads();
+            BPHASE_MARK(4);
+            if (gsm[0] | gsm[1] | gsm[2] | gsm[3]) {
+                // modified Gram-Schmidt inside clusters of close eigenvalues (rare): one warp, lanes share the rows
+                if (warp == 0) {
+                    for (int i = 1; i < d; ++i) {
+                        if (!((gsm[i >> 5] >> (i & 31)) & 1u)) continue;
+                        for (int j = i - 1; j >= 0; --j) {
+                            double dot = 0.0;
+                            for (int k = lane; k < d; k += 32) dot = fma(zs[(size_t)k * LDV + i], zs[(size_t)k * LDV + j], dot);
+                            dot = warp_sum(dot);
+                            for (int k = lane; k < d; k += 32) zs[(size_t)k * LDV + i] = fma(-dot, zs[(size_t)k * LDV + j], zs[(size_t)k * LDV + i]);
+                            __syncwarp();
+                            if (!((gsm[j >> 5] >> (j & 31)) & 1u)) break;      // j was the first member of the cluster
+                        }
+                        double s2 = 0.0;
+                        for (int k = lane; k < d; k += 32) s2 = fma(zs[(size_t)k * LDV + i], zs[(size_t)k * LDV + i], s2);
+                        s2 = warp_sum(s2);
+                        if (!(s2 > 0.25)) { if (lane == 0) ired[2] = 1; s2 = 1.0; }   // the recurrences returned (nearly) the same vector
+                        const double rn = 1.0 / sqrt(s2);
+                        for (int k = lane; k < d; k += 32) zs[(size_t)k * LDV + i] *= rn;
+                        __syncwarp();
+                    }
+                }
+                __syncthreads();
+            }
+            if (tid == 0 && ired[2]) {                       // numerically degenerate / overflowed: the generic kernel redoes the point
+                const int slot = atomicAdd(a.fb_count, 1);
+                a.fb_list[slot] = (int)b;
+                atomicAdd(pv.stats + 0, 1ULL);
+            }
+            if (dense) {
+                // ---- V = Q Z on the FP64 tensor path: warp w owns the row tiles w, w + NW, ...; A = Q fragments straight from
+                // global memory (column-major: 8 consecutive rows of one column are 64 contiguous bytes), B = Z from shared
+                // memory.  The C tiles stay in registers until every warp is done reading Z, then replace it.
+                if constexpr (D <= 84) {
+                    constexpr int MTW = L::MTW, KT = KP / 4, NT8 = (D + 7) / 8;
+                    const int lg = lane >> 2, lt = lane & 3;
+                    const double* qb = a.bs.qmat + (size_t)b * d * d;
+                    const unsigned zaddr = smem_addr(zs) + (unsigned)((lt * LDV + lg) * 8);
+                    double2 acc[MTW][NT8];
+#pragma unroll
+                    for (int m = 0; m < MTW; ++m)
+#pragma unroll
+                        for (int n = 0; n < NT8; ++n) acc[m][n] = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int m = 0; m < MTW; ++m) {
+                        const int r0 = 8 * (warp + m * NW);
+                        if (r0 < d) {
+                            const int r = r0 + lg;
+                            double af[KT];
+#pragma unroll
+                            for (int kt = 0; kt < KT; ++kt) {
+                                const int k = 4 * kt + lt;
+                                af[kt] = (r < d && k < d) ? qb[(size_t)k * d + r] : 0.0;
+                            }
+#pragma unroll
+                            for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+                                for (int n = 0; n < NT8; ++n)
+                                    dmma884(acc[m][n], af[kt], lds64(zaddr + (unsigned)((4 * kt * LDV + 8 * n) * 8)));
+                        }
+                    }
+                    __syncthreads();                         // every warp has read Z
+#pragma unroll
+                    for (int m = 0; m < MTW; ++m) {
+                        const int r = 8 * (warp + m * NW) + lg;
+                        if (r < d) {
+#pragma unroll
+                            for (int n = 0; n < NT8; ++n) {
+                                const int c0 = 8 * n + 2 * lt;
+                                if (c0 < d) zs[(size_t)r * LDV + c0] = acc[m][n].x;
+                                if (c0 + 1 < d) zs[(size_t)r * LDV + c0 + 1] = acc[m][n].y;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < D; ++j) v[j] = (row < d) ? zs[(size_t)row * LDV + j] : 0.0;
+            __syncthreads();                                 // sa / sb / sib (in vec) and Z are dead from here on
+            BPHASE_MARK(5);
+        } else {
         const long long batch = b >> 5;
         const int blane = (int)(b & 31);
         const int nr_all = a.bs.nrounds[batch];
@@ -467,7 +689,6 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) replay
         BPHASE_START();
         if (tid == 0) ired[0] = 0;
         // ---- V <- I or Q (column-major: coalesced over the rows)
-        double v[D];
         if (dense && row < d) {
             const double* q = a.bs.qmat + (size_t)b * d * d + row;
 #pragma unroll
@@ -590,6 +811,8 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) replay
         cp_async_wait<0>();
         __syncthreads();                                 // replay region is dead from here on
         BPHASE_MARK(5);
+
+        }
 
         // ---- c = V[0,:], eigenvalues, unit phase steps
         if (row == 0) {
@@ -958,10 +1181,10 @@ size_t replay_smem_bytes(int maxr, int T) {
     return (size_t)(L::PHASED + ((phased + 1) & ~1) + ((T + 1) & ~1)) * sizeof(double);
 }
 
-template <int D, int NW, int MINB, int GS>
+template <int D, int NW, int MINB, int GS, bool DIRECT = false>
 int launch_replay_t(const RegArgs& a, int sms, cudaStream_t st) {
     const size_t smem = replay_smem_bytes<D, NW>(a.bs.maxr, a.pv.T);
-    auto kern = replay_reg_kernel<D, NW, MINB, GS>;
+    auto kern = replay_reg_kernel<D, NW, MINB, GS, DIRECT>;
     QTET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     QTET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int per_sm = 0;
@@ -1034,10 +1257,26 @@ int launch_hh_reg(const ProblemView& pv, const double* chis, int64_t n, const Bi
     return QTET_EUNSUPPORTED;
 }
 
+int bigreg_direct_max_dim(bool dense) { return dense ? 84 : 101; }
+
 int launch_replay_reg(const ProblemView& pv, const double* chis, int64_t n, int site, const BigStream& bs,
                       const unsigned short* pair_tab, double* loss, double* grad, int32_t* tstar, double* trace, int sms,
-                      cudaStream_t st) {
-    const RegArgs a = make_args(pv, chis, n, site, bs, pair_tab, loss, grad, tstar, trace);
+                      cudaStream_t st, bool direct, int* fb_list, int* fb_count) {
+    RegArgs a = make_args(pv, chis, n, site, bs, pair_tab, loss, grad, tstar, trace);
+    a.fb_list = fb_list; a.fb_count = fb_count;
+    if (direct) {
+        switch (bigreg_padded_dim(pv.d)) {
+            case 16: return launch_replay_t<16, 1, 8, 4, true>(a, sms, st);
+            case 32: return launch_replay_t<32, 1, 8, 4, true>(a, sms, st);
+            case 48: return launch_replay_t<48, 2, 4, 4, true>(a, sms, st);
+            case 66: return launch_replay_t<66, 3, 4, 4, true>(a, sms, st);
+            case 84: return launch_replay_t<84, 3, 2, 4, true>(a, sms, st);
+            case 101: return launch_replay_t<101, 4, 2, 2, true>(a, sms, st);
+            default: break;
+        }
+        set_error("register-resident direct kernel: dimension out of range");
+        return QTET_EUNSUPPORTED;
+    }
     switch (bigreg_padded_dim(pv.d)) {
         case 16: return launch_replay_t<16, 1, 8, 4>(a, sms, st);
         case 32: return launch_replay_t<32, 1, 8, 4>(a, sms, st);

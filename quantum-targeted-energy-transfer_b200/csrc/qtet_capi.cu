@@ -46,13 +46,17 @@ int ensure_scratch(qtet_problem* p, size_t bytes) {
 }
 
 static int auto_path(const ProblemView& v) {
-    if (direct_eligible(v)) return QTET_PATH_DIRECT;
+    if (direct_eligible(v) || big_direct_eligible(v)) return QTET_PATH_DIRECT;
     return (split_eligible(v) || big_eligible(v)) ? QTET_PATH_SPLIT : QTET_PATH_GENERIC;
 }
 
 int loss_grad_dispatch(qtet_problem* p, const double* chis, int64_t B, int site, double* loss,
                        double* grad, int32_t* tstar, double* trace, cudaStream_t st, const ChunkHook* hook,
                        const int* n_dev) {
+    if (p->path == QTET_PATH_DIRECT && !direct_eligible(p->view)) {
+        if (n_dev) { set_error("a device-side batch size is only supported on the d <= 32 direct path"); return QTET_EINVAL; }
+        return launch_big_direct(p->view, &p->big_ws, chis, B, site, loss, grad, tstar, trace, st, p->prof.on ? &p->prof : nullptr, hook);
+    }
     if (p->path == QTET_PATH_DIRECT)
         return launch_direct(p->view, &p->direct_ws, chis, B, n_dev, site, loss, grad, tstar, trace, st, p->prof.on ? &p->prof : nullptr, hook);
     if (n_dev) { set_error("a device-side batch size is only supported on the direct path"); return QTET_EINVAL; }
@@ -214,7 +218,7 @@ int qtet_set_path(qtet_problem* p, int path) {
     if (!p) { set_error("null handle"); return QTET_EINVAL; }
     if (path == QTET_PATH_AUTO) { p->path = auto_path(p->view); return QTET_OK; }
     if (path == QTET_PATH_DIRECT) {
-        if (!direct_eligible(p->view)) { set_error("direct path needs a tridiagonal H with non-zero hopping and dim <= 32"); return QTET_EUNSUPPORTED; }
+        if (!direct_eligible(p->view) && !big_direct_eligible(p->view)) { set_error("direct path needs non-zero hopping and dim <= 101 (tridiagonal H) / 84 (dense H)"); return QTET_EUNSUPPORTED; }
         p->path = path;
         return QTET_OK;
     }
@@ -239,8 +243,7 @@ int qtet_problem_reserve(qtet_problem* p, int64_t B) {
     const size_t adam = (size_t)B * (5 * f * 8 + 3 * 8 + f * 4 + 4 * 4) + 16 * 256;
     int rc = ensure_scratch(p, host_call > adam ? host_call : adam);
     if (rc) return rc;
-    if (p->path == QTET_PATH_DIRECT && B <= (1LL << 22)) return direct_reserve(p->view, &p->direct_ws, B, true);
-    if (p->path == QTET_PATH_DIRECT) return direct_reserve(p->view, &p->direct_ws, B, false);
+    if (p->path == QTET_PATH_DIRECT && direct_eligible(p->view)) return direct_reserve(p->view, &p->direct_ws, B, B <= (1LL << 22));
     return QTET_OK;
 }
 

@@ -119,6 +119,11 @@ bool big_eligible(const ProblemView& pv);
 int launch_big(const ProblemView& pv, BigWorkspace** ws, const double* chis, int64_t B, int site, double* loss,
                double* grad, int32_t* tstar, double* trace, cudaStream_t st, Profiler* prof = nullptr);
 void big_workspace_free(BigWorkspace* ws);
+// large-d direct path (eigenvectors by recurrences, no rotation stream); shares the workspace type
+bool big_direct_eligible(const ProblemView& pv);
+int launch_big_direct(const ProblemView& pv, BigWorkspace** ws, const double* chis, int64_t B, int site, double* loss,
+                      double* grad, int32_t* tstar, double* trace, cudaStream_t st, Profiler* prof = nullptr,
+                      const ChunkHook* hook = nullptr);
 
 int launch_argmin(const double* v, int64_t B, double* min_out, int64_t* idx_out, cudaStream_t st);
 
