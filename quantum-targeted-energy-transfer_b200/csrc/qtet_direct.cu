@@ -434,6 +434,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) direct_kernel(SplitArgs a) {
         }
         int ncol = __reduce_max_sync(0xffffffffu, nsig);
         if (ncol < 1) ncol = 1;
+#ifdef QTET_PHASE_TIMING
+        if (lane == 0) atomicAdd(pv.stats + 3, (unsigned long long)ncol);      // debug builds: sum of the per-warp column counts
+#endif
         __syncwarp();
         double v[R][D];
 #pragma unroll

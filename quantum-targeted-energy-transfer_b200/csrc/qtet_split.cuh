@@ -197,16 +197,28 @@ __device__ __forceinline__ void evolve_and_grad(const SplitArgs& a, double (&v)[
         double pr0[R], pi0[R], pr1[R], pi1[R];
 #pragma unroll
         for (int kk = 0; kk < R; ++kk) { pr0[kk] = pi0[kk] = pr1[kk] = pi1[kk] = 0.0; }
+        // columns in groups of four with ONE warp-uniform exit test per group (PERM: the columns from ncol on have |c_i| <= 1e-19
+        // and z_i = 0): inside a group the loads run ahead of the FMAs, a test per column would serialise them
 #pragma unroll
-        for (int i = 0; i < D; ++i) {
-            if (PERM && i >= ncol) break;               // warp-uniform: the remaining columns have |c_i| <= 1e-19
-            const double2 za = zb0[i], zc = zb1[i];
+        for (int i0 = 0; i0 < D; i0 += 4) {
+            if (PERM && i0 >= ncol) break;
+            double2 za[4], zc[4];
 #pragma unroll
-            for (int kk = 0; kk < R; ++kk) {
-                pr0[kk] = fma(v[kk][i], za.x, pr0[kk]);
-                pi0[kk] = fma(v[kk][i], za.y, pi0[kk]);
-                pr1[kk] = fma(v[kk][i], zc.x, pr1[kk]);
-                pi1[kk] = fma(v[kk][i], zc.y, pi1[kk]);
+            for (int ii = 0; ii < 4; ++ii) {
+                if (i0 + ii < D) { za[ii] = zb0[i0 + ii]; zc[ii] = zb1[i0 + ii]; }
+            }
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) {
+                const int i = i0 + ii;
+                if (i < D) {
+#pragma unroll
+                    for (int kk = 0; kk < R; ++kk) {
+                        pr0[kk] = fma(v[kk][i], za[ii].x, pr0[kk]);
+                        pi0[kk] = fma(v[kk][i], za[ii].y, pi0[kk]);
+                        pr1[kk] = fma(v[kk][i], zc[ii].x, pr1[kk]);
+                        pi1[kk] = fma(v[kk][i], zc[ii].y, pi1[kk]);
+                    }
+                }
             }
         }
         double part0 = 0.0, part1 = 0.0;
@@ -265,11 +277,17 @@ __device__ __forceinline__ void evolve_and_grad(const SplitArgs& a, double (&v)[
 #pragma unroll
         for (int kk = 0; kk < R; ++kk) { pr[kk] = 0.0; pi[kk] = 0.0; }
 #pragma unroll
-        for (int i = 0; i < D; ++i) {
-            if (PERM && i >= ncol) break;
-            const double2 z = zb[i];
+        for (int i0 = 0; i0 < D; i0 += 4) {
+            if (PERM && i0 >= ncol) break;
 #pragma unroll
-            for (int kk = 0; kk < R; ++kk) { pr[kk] = fma(v[kk][i], z.x, pr[kk]); pi[kk] = fma(v[kk][i], z.y, pi[kk]); }
+            for (int ii = 0; ii < 4; ++ii) {
+                const int i = i0 + ii;
+                if (i < D) {
+                    const double2 z = zb[i];
+#pragma unroll
+                    for (int kk = 0; kk < R; ++kk) { pr[kk] = fma(v[kk][i], z.x, pr[kk]); pi[kk] = fma(v[kk][i], z.y, pi[kk]); }
+                }
+            }
         }
 #pragma unroll
         for (int kk = 0; kk < R; ++kk) { wcr[kk] = wsite[kk] * pr[kk]; wci[kk] = -wsite[kk] * pi[kk]; }

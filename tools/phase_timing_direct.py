@@ -39,3 +39,8 @@ print(f"B={B} N={N} total step {e0.elapsed_time(e1):.3f} ms ; warp-cycles per po
 for i, n in enumerate(names):
     print(f"  {n:34s} {out[i]/B*4:10.1f} cycles/warp-task  {100*out[i]/tot:5.1f}%")
 print(f"  {'sum':34s} {tot/B*4:10.1f}")
+
+import ctypes as C
+raw = (C.c_int64 * 4)()
+_native.lib.qtet_stats(prob._h, raw, 0)
+print("sum of ncol over warp-tasks:", raw[3], " (3 passes over the grid) -> mean ncol =", raw[3] / (3 * B / 4))
