@@ -294,6 +294,134 @@ __global__ void __launch_bounds__(kWarpsBig * 32) ql_scalar_big_kernel(BigQlArgs
 // eigenvector kernel starts its recurrences from.  No rotation stream: 16 d bytes per point leave this kernel instead of
 // ~(d^2 + 8 d) * 16.
 // ------------------------------------------------------------------------------------------------
+#ifndef QTET_KE_PWK
+#define QTET_KE_PWK 0     // 1: square-root-free rational QL (dsterf recurrence); 0: rotation-based implicit QL
+#endif
+#if QTET_KE_PWK
+__device__ __forceinline__ double fast_rcp_big(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+// off-diagonal negligible, tested on its square:  |e_k| <= eps (|d_k| + |d_k+1|)
+__device__ __forceinline__ bool tiny_sq(double e2v, double dk, double dk1) {
+    const double tst = kEps * (fabs(dk) + fabs(dk1));
+    return e2v <= tst * tst;
+}
+
+// Square-root-free rational QL (Pal-Walker-Kahan / LAPACK dsterf) on the squared off-diagonals, see qtet_direct.cu: the kernel
+// is a latency chain per point, and this recurrence's chain is about half as long as the rotation-based one.
+template <bool LOCAL>
+__global__ void __launch_bounds__(kWarpsBig * 32) eig_scalar_big_kernel(BigQlArgs a) {
+    extern __shared__ double sm[];
+    const ProblemView& pv = a.pv;
+    const int d = pv.d, f = pv.f;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    QlLaneBig<LOCAL> t;                                   // of(k) holds the SQUARED off-diagonal here
+    t.arr = LOCAL ? nullptr : sm + (size_t)warp * 2 * d * 32 + lane;
+    t.d = d;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.overflow_count = 0;      // the eigenvector kernel (stream-ordered after us) appends
+    const long long nbatch = (a.n + 31) / 32;
+    for (long long batch = (long long)blockIdx.x * kWarpsBig + warp; batch < nbatch; batch += (long long)gridDim.x * kWarpsBig) {
+        const long long p = batch * 32 + lane;
+        const bool valid = p < a.n;
+        const long long pc = valid ? p : a.n - 1;
+        double hchi[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hchi[k] = (k < f && !a.use_tri) ? 0.5 * a.chis[pc * f + k] : 0.0;
+        double sum = 0.0;
+        for (int m = 0; m < d; ++m) {
+            double acc, off;
+            if (a.use_tri) {
+                acc = a.bs.tri_d[pc * d + m];
+                off = (m < d - 1) ? a.bs.tri_e[pc * d + m] : 0.0;
+            } else {
+                acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (k < f) {
+                        const double n = pv.occ[m * f + k];
+                        acc = acc + (pv.omegas[k] * n + hchi[k] * (n * n));
+                    }
+                }
+                off = (m < d - 1) ? pv.offd[m] : 0.0;
+            }
+            t.dg(m) = acc;
+            t.of(m) = off * off;
+            sum += acc;
+        }
+        const double mean = sum / (double)d;
+        for (int m = 0; m < d; ++m) {
+            const double x = t.dg(m) - mean;
+            t.dg(m) = x;
+            if (valid) a.bs.adiag[p * d + m] = x;         // what the recurrences of the eigenvector kernel run on
+        }
+        Mask128 small;
+        small.set(d - 1);
+        for (int k = 0; k < d - 1; ++k)
+            if (tiny_sq(t.of(k), t.dg(k), t.dg(k + 1))) small.set(k);
+        int l = 0, iter = 0;
+        bool failed = false;
+        while (true) {
+            const int lnew = small.first_clear_ge(l, d - 1);
+            if (lnew < 0) break;
+            if (lnew != l) iter = 0;
+            l = lnew;
+            const int m = small.first_set_ge(l);
+            if (++iter > 60) { failed = true; break; }
+            double sigma;
+            {
+                const double pl = t.dg(l), rte = sqrt(t.of(l));
+                const double sg = (t.dg(l + 1) - pl) / (2.0 * rte);
+                const double rr = sqrt(fma(sg, sg, 1.0));
+                sigma = pl - rte / (sg + copysign(rr, sg));
+            }
+            double c = 1.0, s = 0.0, gamma = t.dg(m) - sigma, pp = gamma * gamma, dnext = 0.0;
+            double alpha = t.dg(m - 1), bb = t.of(m - 1);   // loaded a plane ahead of their use
+            WalkBit fb; fb.at(m);
+            for (int i = m - 1; i >= l; --i) {
+                const int in = (i > l) ? i - 1 : i;
+                const double alpha_n = t.dg(in), bb_n = t.of(in);
+                const double r = pp + bb;
+                if (!(r > 1e-290)) { failed = true; break; }
+                const double e2new = s * r;
+                const double rinv = fast_rcp_big(r), pinv = fast_rcp_big(pp);
+                const double oldc = c;
+                c = pp * rinv; s = bb * rinv;
+                const double oldgam = gamma;
+                gamma = fma(c, alpha - sigma, -(s * oldgam));
+                const double dnew = oldgam + (alpha - gamma);
+                t.dg(i + 1) = dnew;
+                pp = (c != 0.0) ? (gamma * gamma) * (r * pinv) : oldc * bb;
+                if (i != m - 1) {
+                    t.of(i + 1) = e2new;
+                    put_bit(small, fb, tiny_sq(e2new, dnew, dnext));
+                }
+                fb.down();
+                dnext = dnew; alpha = alpha_n; bb = bb_n;
+            }
+            if (failed) break;
+            const double e2l = s * pp, dl = sigma + gamma;
+            t.of(l) = e2l; t.dg(l) = dl;
+            small.put(l, tiny_sq(e2l, dl, dnext));
+        }
+        for (int i = 1; i < d; ++i) {                      // ascending order (insertion sort; the QL output is close to sorted)
+            const double x = t.dg(i);
+            int j = i - 1;
+            while (j >= 0 && t.dg(j) > x) { t.dg(j + 1) = t.dg(j); --j; }
+            t.dg(j + 1) = x;
+        }
+        if (valid) {
+            if (failed) t.dg(0) = __longlong_as_double(0x7ff8000000000000LL);      // poisons the point: it takes the fallback
+            for (int m = 0; m < d; ++m) a.bs.ev[p * d + m] = t.dg(m);
+        }
+        __syncwarp();
+    }
+}
+
+#else
 template <bool LOCAL>
 __global__ void __launch_bounds__(kWarpsBig * 32) eig_scalar_big_kernel(BigQlArgs a) {
     extern __shared__ double sm[];
@@ -393,6 +521,8 @@ __global__ void __launch_bounds__(kWarpsBig * 32) eig_scalar_big_kernel(BigQlArg
         __syncwarp();
     }
 }
+
+#endif
 
 }  // namespace
 

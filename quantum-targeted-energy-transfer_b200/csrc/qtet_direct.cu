@@ -47,6 +47,136 @@ __device__ __forceinline__ double diag_entry(const double* lin, const double* qu
     return acc;
 }
 
+#ifndef QTET_REC_ROLLED
+#define QTET_REC_ROLLED 1  // 1: the three recurrence passes of K_D as rolled loops (small code), 0: fully unrolled with register-resident constants
+#endif
+#ifndef QTET_KE_PWK
+#define QTET_KE_PWK 0     // 1: square-root-free rational QL (dsterf recurrence) in K_E; 0: rotation-based implicit QL
+#endif
+#if QTET_KE_PWK
+// ------------------------------------------------------------------------------------------------
+// K_E: thread-per-point QL, eigenvalues only.  diag/off in shared memory as [2k + {0,1}][lane].
+//
+// Square-root-free rational QL (Pal-Walker-Kahan, the LAPACK dsterf recurrence) on the SQUARED off-diagonals: a plane costs
+// two reciprocals and ~12 FP64 operations with a dependency chain of  r = p + e2 -> 1/r -> c -> gamma -> p'  (~65 cycles)
+// where the rotation-based sweep of qtet_split.cu needs rsqrt and ~22 operations (~120 cycles).  The kernel is a pure latency
+// chain (one point per thread, five warps per scheduler), so the chain length IS its run time.
+// ------------------------------------------------------------------------------------------------
+struct PwkLane {
+    double* arr;       // diag k at arr[64 k], SQUARED off-diagonal k at arr[64 k + 32]
+    int d;
+    __device__ __forceinline__ double& dg(int k) const { return arr[64 * k]; }
+    __device__ __forceinline__ double& e2(int k) const { return arr[64 * k + 32]; }
+    // off-diagonal k negligible:  |e_k| <= eps (|d_k| + |d_k+1|), tested on the squares
+    __device__ __forceinline__ static bool tiny(double e2v, double dk, double dk1) {
+        const double tst = kEps * (fabs(dk) + fabs(dk1));
+        return e2v <= tst * tst;
+    }
+    __device__ __forceinline__ unsigned scan_small() const {
+        unsigned small = 1u << (d - 1);
+        for (int k = 0; k < d - 1; ++k)
+            if (tiny(e2(k), dg(k), dg(k + 1))) small |= 1u << k;
+        return small;
+    }
+};
+
+__global__ void __launch_bounds__(kWarpsE * 32) eig_scalar_kernel(SplitArgs a) {
+    extern __shared__ double sm[];
+    const ProblemView& pv = a.pv;
+    const int d = pv.d, f = pv.f;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    PwkLane t;
+    t.arr = sm + (size_t)warp * 2 * d * 32 + lane;
+    t.d = d;
+    const long long n = effective_n(a);
+    const long long nbatch = (n + 31) / 32;
+    const unsigned below_top = lowmask(d - 1);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.fb_count = 0;    // K_D of this chunk (stream-ordered after us) appends to the list
+    for (long long batch = (long long)blockIdx.x * kWarpsE + warp; batch < nbatch; batch += (long long)gridDim.x * kWarpsE) {
+        const long long p = batch * 32 + lane;
+        const bool valid = p < n;
+        const long long pc = valid ? p : n - 1;
+        double chi[kMaxF];
+#pragma unroll
+        for (int k = 0; k < kMaxF; ++k) chi[k] = (k < f) ? a.chis[pc * f + k] : 0.0;
+        double sum = 0.0;
+        for (int m = 0; m < d; ++m) {
+            const double acc = diag_entry(pv.lin, pv.quad, chi, f, m);
+            const double off = (m < d - 1) ? pv.offd[m] : 0.0;
+            t.dg(m) = acc;
+            t.e2(m) = off * off;
+            sum = __dadd_rn(sum, acc);
+        }
+        const double mean = __ddiv_rn(sum, (double)d);       // global phase: subtract the mean of the diagonal
+        for (int m = 0; m < d; ++m) t.dg(m) = __dsub_rn(t.dg(m), mean);
+
+        unsigned small = t.scan_small();
+        int l = 0, iter = 0;
+        bool failed = false;
+        while (true) {
+            const unsigned alive = (~small) & below_top & ~lowmask(l);
+            if (alive == 0u) break;
+            const int lnew = __ffs(alive) - 1;
+            if (lnew != l) iter = 0;
+            l = lnew;
+            const int m = l + __ffs(small >> l) - 1;           // first negligible off-diagonal above l
+            if (++iter > 60) { failed = true; break; }
+            // Wilkinson shift from the leading 2 x 2 block of [l, m]
+            double sigma;
+            {
+                const double pl = t.dg(l), rte = sqrt(t.e2(l));
+                const double sg = (t.dg(l + 1) - pl) / (2.0 * rte);
+                const double rr = sqrt(fma(sg, sg, 1.0));
+                sigma = pl - rte / (sg + copysign(rr, sg));
+            }
+            double c = 1.0, s = 0.0, gamma = t.dg(m) - sigma, pp = gamma * gamma, dnext = 0.0;
+            double* q = t.arr + 64 * (m - 1);                 // &dg(i)
+            double alpha = q[0], bb = q[32];                  // d_i, e2_i of the coming plane, loaded a plane ahead
+            unsigned fbit = 1u << m;                          // flag of the off-diagonal the plane finalises (i + 1)
+            for (int i = m - 1; i >= l; --i, q -= 64) {
+                const double* qn = (i > l) ? q - 64 : q;
+                const double alpha_n = qn[0], bb_n = qn[32];
+                const double r = pp + bb;
+                if (!(r > 1e-290)) { failed = true; break; }  // underflow of the whole block: hand the point to the fallback
+                const double e2new = s * r;                   // squared off-diagonal i + 1 (s = 0 on the first plane: e2(m) stays)
+                const double rinv = fast_rcp(r), pinv = fast_rcp(pp);
+                const double oldc = c;
+                c = pp * rinv; s = bb * rinv;
+                const double oldgam = gamma;
+                gamma = fma(c, alpha - sigma, -(s * oldgam));
+                const double dnew = oldgam + (alpha - gamma);
+                q[64] = dnew;                                 // dg(i + 1)
+                pp = (c != 0.0) ? (gamma * gamma) * (r * pinv) : oldc * bb;
+                if (i != m - 1) {
+                    q[96] = e2new;                            // e2(i + 1)
+                    small = PwkLane::tiny(e2new, dnew, dnext) ? (small | fbit) : (small & ~fbit);
+                }
+                fbit >>= 1;
+                dnext = dnew; alpha = alpha_n; bb = bb_n;
+            }
+            if (failed) break;
+            const double e2l = s * pp, dl = sigma + gamma;
+            t.e2(l) = e2l; t.dg(l) = dl;
+            const unsigned bit = 1u << l;
+            small = PwkLane::tiny(e2l, dl, dnext) ? (small | bit) : (small & ~bit);
+        }
+        // ascending order (insertion sort; the QL output is close to sorted)
+        for (int i = 1; i < d; ++i) {
+            const double x = t.dg(i);
+            int j = i - 1;
+            while (j >= 0 && t.dg(j) > x) { t.dg(j + 1) = t.dg(j); --j; }
+            t.dg(j + 1) = x;
+        }
+        if (valid) {
+            // a QL that did not converge poisons the point: K_D sees the NaN and hands the point to the generic kernel
+            if (failed) t.dg(0) = __longlong_as_double(0x7ff8000000000000LL);
+            for (int m = 0; m < d; ++m) a.ev[p * d + m] = t.dg(m);
+        }
+        __syncwarp();
+    }
+}
+
+#else
 // ------------------------------------------------------------------------------------------------
 // K_E: thread-per-point QL, eigenvalues only.  diag/off in shared memory as [2k + {0,1}][lane].
 // ------------------------------------------------------------------------------------------------
@@ -139,6 +269,8 @@ __global__ void __launch_bounds__(kWarpsE * 32) eig_scalar_kernel(SplitArgs a) {
     }
 }
 
+#endif
+
 template <int D, int G>
 struct DLayout {
     using L = BLayout<D, G>;
@@ -147,7 +279,7 @@ struct DLayout {
     static constexpr int VT = PPW * D * LDV;                           // double [PPW][D rows][LDV]
     static constexpr int PHASED = (VT > L::GRAD ? VT : L::GRAD);      // the transpose buffer aliases the gradient buffers
     static constexpr int PER_WARP = ((PHASED + L::ZB + PPW * D) + 1) & ~1;
-    static constexpr int CONSTS = ((D * (1 + kMaxF)) + 1) & ~1;       // per CTA: lin, quad
+    static constexpr int CONSTS = ((D * (3 + kMaxF)) + 1) & ~1;       // per CTA: lin, quad, b_k, 1 / b_k
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -167,7 +299,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) direct_kernel(SplitArgs a) {
     // CTA-wide constants
     double* slin = sm;                     // [D]
     double* squad = sm + D;                // [D][f]
+    double* sb = sm + D * (1 + kMaxF);     // [D] b_k = H[k+1,k] (0 for k >= d-1)
+    double* sib = sb + D;                  // [D] 1 / b_k        (0 for k >= d-1)
     for (int k = threadIdx.x; k < D; k += WARPS * 32) {
+        sb[k] = (k < 32) ? a.boff[k] : 0.0;
+        sib[k] = (k < 32) ? a.iboff[k] : 0.0;
         slin[k] = (k < d) ? pv.lin[k] : 0.0;
         for (int s = 0; s < f; ++s) squad[k * f + s] = (k < d) ? pv.quad[k * f + s] : 0.0;
     }
@@ -252,6 +388,104 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) direct_kernel(SplitArgs a) {
         double* colp[RZ];
 #pragma unroll
         for (int t = 0; t < RZ; ++t) { const int i = q + t * G; colp[t] = vp + ((i < D) ? i : (D - 1)); }   // i >= D: nothing is stored
+#if QTET_REC_ROLLED
+        // ROLLED loops: the three passes are ~40 instructions each instead of ~1700 unrolled ones.  The kernel is a 7000-
+        // instruction straight line per task and `no_instruction` was its third stall reason (profiles/r2_*): what need not be
+        // unrolled (nothing here indexes a register array) is not.  Every operand of step k+1 is loaded during step k.
+        // from the bottom: q_{k-1} = ((lam - a_k) q_k - b_k q_{k+1}) / b_{k-1},  q_{d-1} = 1
+        {
+            double qn[RZ], qc[RZ];
+#pragma unroll
+            for (int t = 0; t < RZ; ++t) {
+                qn[t] = 0.0; qc[t] = (D - 1 == d - 1) ? 1.0 : 0.0;
+                if (q + t * G < D) colp[t][(D - 1) * LDV] = qc[t];
+            }
+            double ak = ap[D - 1], bk = sb[D - 1], ibm = sib[D - 2];
+#pragma unroll 2
+            for (int k = D - 1; k >= 1; --k) {
+                const int kn = (k >= 2) ? k - 1 : 1;
+                const double ak_n = ap[kn], bk_n = sb[kn], ibm_n = sib[kn - 1];
+#pragma unroll
+                for (int t = 0; t < RZ; ++t) {
+                    double val = fma(lam[t] - ak, qc[t], -(bk * qn[t])) * ibm;
+                    if (!EXACT && k - 1 == d - 1) val = 1.0;
+                    qn[t] = qc[t]; qc[t] = val;
+                    if (q + t * G < D) colp[t][(k - 1) * LDV] = val;
+                }
+                ak = ak_n; bk = bk_n; ibm = ibm_n;
+            }
+        }
+        __syncwarp();
+        PHASE_MARK(11);
+        // from the top: p_{k+1} = ((lam - a_k) p_k - b_{k-1} p_{k-1}) / b_k,  p_0 = 1; join row r = argmax |p_k q_k|
+        double invp[RZ], invq[RZ];
+        int rj[RZ];
+        {
+            double pm[RZ], pcur[RZ], best[RZ], pr[RZ], qr[RZ], qk1[RZ];
+#pragma unroll
+            for (int t = 0; t < RZ; ++t) {
+                const double q0 = colp[t][0];
+                pm[t] = 0.0; pcur[t] = 1.0; best[t] = fabs(q0); rj[t] = 0; pr[t] = 1.0; qr[t] = q0;
+                qk1[t] = colp[t][LDV];
+            }
+            double ak = ap[0], bm = 0.0, ib = sib[0];
+#pragma unroll 2
+            for (int k = 0; k < D - 1; ++k) {
+                const int kn = (k + 1 < D - 1) ? k + 1 : k;
+                const double ak_n = ap[kn], bm_n = sb[kn - 1 >= 0 ? kn - 1 : 0], ib_n = sib[kn];
+                double qn2[RZ];
+#pragma unroll
+                for (int t = 0; t < RZ; ++t) qn2[t] = colp[t][(kn + 1) * LDV];
+#pragma unroll
+                for (int t = 0; t < RZ; ++t) {
+                    const double pn = fma(lam[t] - ak, pcur[t], -(bm * pm[t])) * ib;
+                    const double prod = fabs(pn * qk1[t]);
+                    if (prod > best[t]) { best[t] = prod; rj[t] = k + 1; pr[t] = pn; qr[t] = qk1[t]; }
+                    pm[t] = pcur[t]; pcur[t] = pn;
+                    qk1[t] = qn2[t];
+                }
+                ak = ak_n; bm = bm_n; ib = ib_n;
+            }
+#pragma unroll
+            for (int t = 0; t < RZ; ++t) { invp[t] = fast_rcp(pr[t]); invq[t] = fast_rcp(qr[t]); }
+        }
+        PHASE_MARK(12);
+        // second pass from the top: z_k = p_k / p_r above the join, q_k / q_r from the join down; 1 / |z| goes to rnbuf
+        // (the scale is applied when the rows are read back)
+        {
+            double pm[RZ], pcur[RZ], ss[RZ], qk[RZ];
+#pragma unroll
+            for (int t = 0; t < RZ; ++t) { pm[t] = 0.0; pcur[t] = 1.0; ss[t] = 0.0; qk[t] = colp[t][0]; }
+            double ak = ap[0], bm = 0.0, ib = sib[0];
+#pragma unroll 2
+            for (int k = 0; k < D; ++k) {
+                const int kn = (k + 1 < D) ? k + 1 : k;
+                const double ak_n = ap[kn], bm_n = sb[kn - 1 >= 0 ? kn - 1 : 0], ib_n = sib[kn];
+                double qn2[RZ];
+#pragma unroll
+                for (int t = 0; t < RZ; ++t) qn2[t] = colp[t][kn * LDV];
+#pragma unroll
+                for (int t = 0; t < RZ; ++t) {
+                    const int i = q + t * G;
+                    const bool above = k < rj[t];
+                    double x = (above ? pcur[t] : qk[t]) * (above ? invp[t] : invq[t]);
+                    if (!EXACT && i >= d) x = (k == i) ? 1.0 : 0.0;             // padded eigen-index: identity column
+                    if (i < D) colp[t][k * LDV] = x;
+                    ss[t] = fma(x, x, ss[t]);
+                    const double pn = fma(lam[t] - ak, pcur[t], -(bm * pm[t])) * ib;     // (unused after the last row)
+                    pm[t] = pcur[t]; pcur[t] = pn;
+                    qk[t] = qn2[t];
+                }
+                ak = ak_n; bm = bm_n; ib = ib_n;
+            }
+#pragma unroll
+            for (int t = 0; t < RZ; ++t) {
+                const int i = q + t * G;
+                if (i < d && !(ss[t] >= 0.5 && ss[t] < 1e300)) { fb = true; ss[t] = 1.0; }   // z_r = 1: |z|^2 >= 1 unless NaN / overflow
+                if (i < D) rnbuf[g * D + i] = (i < d) ? rsqrt_fast(ss[t]) : 1.0;
+            }
+        }
+#else
         // Diagonal and hopping constants in registers for the three passes: with two warps per scheduler nothing hides a
         // load that sits right in front of its use, and phase 0 holds no other large state.  The loads are volatile asm so
         // that they stay up here instead of being re-materialised next to each use.
@@ -341,6 +575,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) direct_kernel(SplitArgs a) {
                 if (i < D) rnbuf[g * D + i] = (i < d) ? rsqrt_fast(ss[t]) : 1.0;
             }
         }
+#endif
         PHASE_MARK(0);
 
         unsigned gm = gsbits;
@@ -411,12 +646,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) direct_kernel(SplitArgs a) {
             for (int t = 0; t < RZ; ++t) {
                 const int i = q + t * G;
                 cabs[t] = (i < D) ? fabs(vp[i] * rnbuf[g * D + i]) : 0.0;
+                if (!(cabs[t] == cabs[t])) cabs[t] = 0.0;             // NaN (overflowed recurrence): the ranks must stay a permutation
                 rank[t] = 0;
                 if (i < D && cabs[t] > kCsig) ++nsig;
             }
 #pragma unroll 1
             for (int j = 0; j < D; ++j) {
-                const double cj = fabs(vp[j] * rnbuf[g * D + j]);
+                double cj = fabs(vp[j] * rnbuf[g * D + j]);
+                if (!(cj == cj)) cj = 0.0;
 #pragma unroll
                 for (int t = 0; t < RZ; ++t) {
                     const int i = q + t * G;

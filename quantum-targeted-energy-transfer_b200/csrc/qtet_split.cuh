@@ -3,7 +3,13 @@
 // shared-memory layout and the phases that follow once V sits in registers -- time evolution, loss, arg-max, and the
 // analytic gradient (HamiltonianLoss.py:204-233, Optimizer.py:85-91).
 #pragma once
+#include <type_traits>
+
 #include "qtet_common.cuh"
+
+#ifndef QTET_EVO_TRIM
+#define QTET_EVO_TRIM 1    // evolution over the significant columns only: 0 off, 1 exit test per group of four, 2 unrolled lengths
+#endif
 
 namespace qtet {
 namespace splitk {
@@ -197,11 +203,39 @@ __device__ __forceinline__ void evolve_and_grad(const SplitArgs& a, double (&v)[
         double pr0[R], pi0[R], pr1[R], pi1[R];
 #pragma unroll
         for (int kk = 0; kk < R; ++kk) { pr0[kk] = pi0[kk] = pr1[kk] = pi1[kk] = 0.0; }
+#if QTET_EVO_TRIM == 2
+        // PERM: only the first ncol columns carry weight (the rest have z_i = 0).  The column loop comes in a few fully unrolled
+        // lengths picked by ONE warp-uniform branch: an exit test inside the loop would keep the loads from running ahead
+        // of the FMAs (measured: no gain from the shorter loop at all with a test per column, 13 % with one per four).
+        auto columns = [&](auto NCc) {
+            constexpr int NC = decltype(NCc)::value;
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                const double2 za = zb0[i], zc = zb1[i];
+#pragma unroll
+                for (int kk = 0; kk < R; ++kk) {
+                    pr0[kk] = fma(v[kk][i], za.x, pr0[kk]);
+                    pi0[kk] = fma(v[kk][i], za.y, pi0[kk]);
+                    pr1[kk] = fma(v[kk][i], zc.x, pr1[kk]);
+                    pi1[kk] = fma(v[kk][i], zc.y, pi1[kk]);
+                }
+            }
+        };
+        if constexpr (PERM && D >= 16) {
+            constexpr int C1 = (D * 2 + 4) / 5, C2 = (D * 3 + 4) / 5, C3 = (D * 4 + 4) / 5;      // ~40 %, 60 %, 80 % of D
+            if (ncol <= C1) columns(std::integral_constant<int, C1>{});
+            else if (ncol <= C2) columns(std::integral_constant<int, C2>{});
+            else if (ncol <= C3) columns(std::integral_constant<int, C3>{});
+            else columns(std::integral_constant<int, D>{});
+        } else {
+            columns(std::integral_constant<int, D>{});
+        }
+#else
         // columns in groups of four with ONE warp-uniform exit test per group (PERM: the columns from ncol on have |c_i| <= 1e-19
         // and z_i = 0): inside a group the loads run ahead of the FMAs, a test per column would serialise them
 #pragma unroll
         for (int i0 = 0; i0 < D; i0 += 4) {
-            if (PERM && i0 >= ncol) break;
+            if (PERM && QTET_EVO_TRIM && i0 >= ncol) break;
             double2 za[4], zc[4];
 #pragma unroll
             for (int ii = 0; ii < 4; ++ii) {
@@ -221,6 +255,7 @@ __device__ __forceinline__ void evolve_and_grad(const SplitArgs& a, double (&v)[
                 }
             }
         }
+#endif
         double part0 = 0.0, part1 = 0.0;
 #pragma unroll
         for (int kk = 0; kk < R; ++kk) {

@@ -62,10 +62,10 @@ def _check(name, O, const, X, site, got, loss_atol=LOSS_ATOL, grad_rtol=GRAD_RTO
 
 
 def config2_rows_and_lines():
-    """>= 65536 points OF the config-2 grid: 40 whole rows, 16 whole columns, the diagonal and the anti-diagonal."""
+    """>= 65536 points OF the config-2 grid: 56 whole rows, 16 whole columns, the diagonal and the anti-diagonal."""
     ax = np.linspace(-10, 10, 1024)
     special = [0, 1, 255, 496, 497, 511, 512, 526, 527, 768, 1022, 1023]      # edges, chi ~ 0 (+-0.0098), chi ~ +-6/N = +-0.3
-    rows = sorted(set(special + list(range(13, 1024, 37))))
+    rows = sorted(set(special + list(range(13, 1024, 23))))
     cols = sorted(set(special + [100, 300, 700, 900]))
     pts = [np.stack([np.full(1024, ax[r]), ax], 1) for r in rows]
     pts += [np.stack([ax, np.full(1024, ax[c])], 1) for c in cols]
