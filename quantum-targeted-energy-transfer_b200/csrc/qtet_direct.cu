@@ -635,42 +635,35 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) direct_kernel(SplitArgs a) {
                 atomicAdd(pv.stats + 0, 1ULL);
             }
         }
-        // ---- order the eigen-indices by |c_i| = |V[0][i]| descending (ties by index): rank of my own indices against all
+        // ---- put the eigen-indices that carry weight first.  c_i = V[0][i] decays fast away from the eigenvalues near the
+        // initial state's energy, so the indices with |c_i| > kCsig form (almost) one window [lo, hi] of the ascending order: the
+        // new order is the CYCLIC SHIFT by lo -- new position i' holds eigen-index (i' + lo) mod D -- and the first
+        // nsig = hi - lo + 1 positions contain every index that matters (14.3 on average on the config-2 grid, against 13.5 for
+        // an exact sort by |c_i|, which costs a 21-step ranking loop per point).
         double* evs = abuf + g * D;                                   // [D] eigenvalues in the new order (ap is dead)
-        int* perm = reinterpret_cast<int*>(abuf + PPW * D) + g * D;   // [D] new position -> eigen-index
-        int nsig = 0;
-        {
-            double cabs[RZ];
-            int rank[RZ];
+        int lo = D, hi = -1;
 #pragma unroll
-            for (int t = 0; t < RZ; ++t) {
-                const int i = q + t * G;
-                cabs[t] = (i < D) ? fabs(vp[i] * rnbuf[g * D + i]) : 0.0;
-                if (!(cabs[t] == cabs[t])) cabs[t] = 0.0;             // NaN (overflowed recurrence): the ranks must stay a permutation
-                rank[t] = 0;
-                if (i < D && cabs[t] > kCsig) ++nsig;
+        for (int t = 0; t < RZ; ++t) {
+            const int i = q + t * G;
+            if (i < d) {
+                const double cabs = fabs(vp[i] * rnbuf[g * D + i]);
+                if (cabs > kCsig) { lo = min(lo, i); hi = max(hi, i); }      // (NaN compares false: handled by the fallback)
             }
-#pragma unroll 1
-            for (int j = 0; j < D; ++j) {
-                double cj = fabs(vp[j] * rnbuf[g * D + j]);
-                if (!(cj == cj)) cj = 0.0;
+        }
 #pragma unroll
-                for (int t = 0; t < RZ; ++t) {
-                    const int i = q + t * G;
-                    if (cj > cabs[t] || (cj == cabs[t] && j < i)) ++rank[t];
-                }
-            }
-            __syncwarp();                                             // everyone is done with ap (aliases evs)
+        for (int o = G / 2; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (hi < lo) { lo = 0; hi = 0; }
+        const int nsig = hi - lo + 1;
+        __syncwarp();                                                 // everyone is done with ap (aliases evs)
 #pragma unroll
-            for (int t = 0; t < RZ; ++t) {
-                const int i = q + t * G;
-                if (i < D) { evs[rank[t]] = lam[t]; perm[rank[t]] = i; }
-            }
-#pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) nsig += __shfl_xor_sync(0xffffffffu, nsig, o);
+        for (int t = 0; t < RZ; ++t) {
+            const int i = q + t * G;
+            if (i < D) { int pos = i - lo; if (pos < 0) pos += D; evs[pos] = lam[t]; }
         }
         int ncol = __reduce_max_sync(0xffffffffu, nsig);
-        if (ncol < 1) ncol = 1;
 #ifdef QTET_PHASE_TIMING
         if (lane == 0) atomicAdd(pv.stats + 3, (unsigned long long)ncol);      // debug builds: sum of the per-warp column counts
 #endif
@@ -678,7 +671,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) direct_kernel(SplitArgs a) {
         double v[R][D];
 #pragma unroll
         for (int i = 0; i < D; ++i) {
-            const int src = perm[i];
+            int src = i + lo;
+            if (src >= D) src -= D;
             const double rn = rnbuf[g * D + src];
 #pragma unroll
             for (int k = 0; k < R; ++k) {

@@ -382,6 +382,7 @@ __device__ __forceinline__ void evolve_and_grad(const SplitArgs& a, double (&v)[
     // [i][o] the row sums below walk through with static indices.
     {
         constexpr int HH = L::HH, U = 5;
+        bool near_any = false;
 #pragma unroll
         for (int t = 0; t < RZ; ++t) {
             const int i = q + t * G;
@@ -409,21 +410,37 @@ __device__ __forceinline__ void evolve_and_grad(const SplitArgs& a, double (&v)[
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         if (o0 + u <= omax) {
-                            double sij = kd[u];
-                            if (fabs(dl[u] * ts) < 1e-2) {
-                                // near-degenerate: Phi_ij = ts f_j (exp(-i x) - 1)/x ; S = Re[(a_i c_j + a_j c_i) Phi_ij]
-                                const int j = jj[u];
-                                double gr, gi;
-                                expm1_over_x(dl[u] * ts, gr, gi);
-                                const double fjr = lvp[2 * PPW * D + j], fji = lvp[3 * PPW * D + j];
-                                const double phr = ts * (fjr * gr - fji * gi), phi = ts * (fjr * gi + fji * gr);
-                                const double c_j = lvp[PPW * D + j];
-                                const double mr = ar_i * c_j + lvp[4 * PPW * D + j] * c_i;
-                                const double mi = ai_i * c_j + lvp[5 * PPW * D + j] * c_i;
-                                sij = mr * phr - mi * phi;
-                            }
-                            sp[D + i * HH + (o0 + u - 1)] = sij;
+                            near_any |= fabs(dl[u] * ts) < 1e-2;
+                            sp[D + i * HH + (o0 + u - 1)] = kd[u];
                         }
+                    }
+                }
+            }
+        }
+        // near-degenerate pairs (|dl t*| < 1e-2, rare): Phi_ij = ts f_j (exp(-i x) - 1)/x ; S = Re[(a_i c_j + a_j c_i) Phi_ij].
+        // Kept out of the hot loop above (a rolled fix-up pass over the lane's pairs, entered only if some lane of the warp saw one):
+        // five inlined copies of this block inside the unrolled pair loop were 170 instructions of mostly-skipped code.
+        if (__any_sync(0xffffffffu, near_any)) {
+#pragma unroll 1
+            for (int t = 0; t < RZ; ++t) {
+                const int i = q + t * G;
+                if (i >= D) continue;
+                const double e_i = lvp[i], c_i = lvp[PPW * D + i], ar_i = lvp[4 * PPW * D + i], ai_i = lvp[5 * PPW * D + i];
+                const int omax = ((D & 1) || i < D / 2) ? HH : HH - 1;
+#pragma unroll 1
+                for (int o = 1; o <= omax; ++o) {
+                    int j = i + o;
+                    if (j >= D) j -= D;
+                    const double x = (e_i - lvp[j]) * ts;
+                    if (fabs(x) < 1e-2) {
+                        double gr, gi;
+                        expm1_over_x(x, gr, gi);
+                        const double fjr = lvp[2 * PPW * D + j], fji = lvp[3 * PPW * D + j];
+                        const double phr = ts * (fjr * gr - fji * gi), phi = ts * (fjr * gi + fji * gr);
+                        const double c_j = lvp[PPW * D + j];
+                        const double mr = ar_i * c_j + lvp[4 * PPW * D + j] * c_i;
+                        const double mi = ai_i * c_j + lvp[5 * PPW * D + j] * c_i;
+                        sp[D + i * HH + (o - 1)] = mr * phr - mi * phi;
                     }
                 }
             }
