@@ -47,6 +47,9 @@ __device__ __forceinline__ double diag_entry(const double* lin, const double* qu
     return acc;
 }
 
+#ifndef QTET_PREFETCH_NEXT
+#define QTET_PREFETCH_NEXT 0  // 1: prefetch the next task's chi / eigenvalues into L1 at the top of a task
+#endif
 #ifndef QTET_REC_ROLLED
 #define QTET_REC_ROLLED 1  // 1: the three recurrence passes of K_D as rolled loops (small code), 0: fully unrolled with register-resident constants
 #endif
@@ -335,6 +338,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) direct_kernel(SplitArgs a) {
         const long long p = task * PPW + g;
         const bool valid = p < n;
         const long long pc = valid ? p : n - 1;
+#if QTET_PREFETCH_NEXT
+        {   // the next task's parameters and eigenvalues into L1 now: its first instructions wait for nothing then
+            const long long pn_ = p + (long long)gridDim.x * WARPS * PPW;
+            if (pn_ < n) {
+                if (q == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.chis + pn_ * f));
+                if (q < 3) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.ev + pn_ * d + q * 8));      // d doubles = up to 3 lines
+            }
+        }
+#endif
 
         // ---- shifted diagonal of my point in shared memory: every lane builds its entries, all lanes sum all of them
         // (the mean must be the bit-identical one K_E subtracted), every lane shifts its entries

@@ -7,6 +7,9 @@
 
 #include "qtet_common.cuh"
 
+#ifndef QTET_EVO_GROUP
+#define QTET_EVO_GROUP 3   // columns per exit test of the trimmed evolution loop
+#endif
 #ifndef QTET_EVO_TRIM
 #define QTET_EVO_TRIM 1    // evolution over the significant columns only: 0 off, 1 exit test per group of four, 2 unrolled lengths
 #endif
@@ -184,7 +187,7 @@ __device__ __forceinline__ void evolve_and_grad(const SplitArgs& a, double (&v)[
     PHASE_MARK(1);
 
     // ---- time evolution: n(t_k) = sum_rows n_site |psi_row(t_k)|^2, running arg-max / arg-min
-    int kbest = 0;
+    int kbest = -1;
     double vbest = 0.0;
     // two samples per pass: every V element is read once for four fmas (operand reuse), the pass overhead halves
     for (int k = 0; k < T; k += 2) {
@@ -234,15 +237,15 @@ __device__ __forceinline__ void evolve_and_grad(const SplitArgs& a, double (&v)[
         // columns in groups of four with ONE warp-uniform exit test per group (PERM: the columns from ncol on have |c_i| <= 1e-19
         // and z_i = 0): inside a group the loads run ahead of the FMAs, a test per column would serialise them
 #pragma unroll
-        for (int i0 = 0; i0 < D; i0 += 4) {
+        for (int i0 = 0; i0 < D; i0 += QTET_EVO_GROUP) {
             if (PERM && QTET_EVO_TRIM && i0 >= ncol) break;
-            double2 za[4], zc[4];
+            double2 za[QTET_EVO_GROUP], zc[QTET_EVO_GROUP];
 #pragma unroll
-            for (int ii = 0; ii < 4; ++ii) {
+            for (int ii = 0; ii < QTET_EVO_GROUP; ++ii) {
                 if (i0 + ii < D) { za[ii] = zb0[i0 + ii]; zc[ii] = zb1[i0 + ii]; }
             }
 #pragma unroll
-            for (int ii = 0; ii < 4; ++ii) {
+            for (int ii = 0; ii < QTET_EVO_GROUP; ++ii) {
                 const int i = i0 + ii;
                 if (i < D) {
 #pragma unroll
@@ -262,18 +265,20 @@ __device__ __forceinline__ void evolve_and_grad(const SplitArgs& a, double (&v)[
             part0 = fma(wsite[kk], fma(pr0[kk], pr0[kk], pi0[kk] * pi0[kk]), part0);
             part1 = fma(wsite[kk], fma(pr1[kk], pr1[kk], pi1[kk] * pi1[kk]), part1);
         }
+        {
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) {
-            part0 += __shfl_xor_sync(0xffffffffu, part0, o);
-            part1 += __shfl_xor_sync(0xffffffffu, part1, o);
+            for (int o = G / 2; o > 0; o >>= 1) {
+                part0 += __shfl_xor_sync(0xffffffffu, part0, o);
+                part1 += __shfl_xor_sync(0xffffffffu, part1, o);
+            }
+            if (a.trace && valid) {
+                if (q == (k % G)) a.trace[p * T + k] = part0;
+                if (k + 1 < T && q == ((k + 1) % G)) a.trace[p * T + k + 1] = part1;
+            }
+            const double key0 = a.acceptor ? part0 : -part0, key1 = a.acceptor ? part1 : -part1;
+            if (kbest < 0 || key0 > vbest) { vbest = key0; kbest = k; }        // first extremum wins ties
+            if (k + 1 < T && key1 > vbest) { vbest = key1; kbest = k + 1; }
         }
-        if (a.trace && valid) {
-            if (q == (k % G)) a.trace[p * T + k] = part0;
-            if (k + 1 < T && q == ((k + 1) % G)) a.trace[p * T + k + 1] = part1;
-        }
-        const double key0 = a.acceptor ? part0 : -part0, key1 = a.acceptor ? part1 : -part1;
-        if (k == 0 || key0 > vbest) { vbest = key0; kbest = k; }        // first extremum wins ties
-        if (k + 1 < T && key1 > vbest) { vbest = key1; kbest = k + 1; }
     }
     if (q == 0 && valid) {
         if (a.loss) a.loss[p] = a.acceptor ? ((double)pv.N - vbest) : -vbest;
