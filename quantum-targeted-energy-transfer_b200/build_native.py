@@ -16,7 +16,7 @@ SUFFIX = os.environ.get("QTET_LIB_SUFFIX", "")
 EXTRA = os.environ.get("QTET_NVCC_DEFS", "").split()
 OBJ = os.path.join(HERE, "build" + SUFFIX)
 LIB = os.path.join(HERE, "lib", f"libqtet_b200{SUFFIX}.so")
-SOURCES = ["qtet_capi.cu", "qtet_generic.cu", "qtet_split.cu", "qtet_direct.cu", "qtet_big.cu", "qtet_bigreg.cu", "qtet_adam.cu"]
+SOURCES = ["qtet_capi.cu", "qtet_generic.cu", "qtet_split.cu", "qtet_direct.cu", "qtet_big.cu", "qtet_bigreg.cu", "qtet_hhfrag.cu", "qtet_adam.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -728,12 +728,17 @@ bool big_direct_eligible(const ProblemView& pv) {
 static long long big_direct_chunk(const ProblemView& pv, long long B) {
     const bool dense = !pv.tridiag;
     const size_t per_point = (size_t)pv.d * 8 * (dense ? 4 : 2) + 4 + (dense ? (size_t)pv.d * pv.d * 8 : 0);
-    long long chunk = ((B + 3) / 4 + 31) / 32 * 32;                 // four chunks per call
-    const long long lo = dense ? 16384 : 65536;
+    // Four chunks per call, but never fewer than 65536 points: the eigenvalue kernel is one thread per point and a pure latency
+    // chain -- with 16384 points it runs 3.5 warps per SM and takes as long as with 65536 (measured: trimer N=10, 4 x 0.84 ms
+    // against 1 x 2.0 ms per 65536 points), and the kernels of consecutive chunks do not overlap anyway (each fills the machine).
+    long long chunk = ((B + 3) / 4 + 31) / 32 * 32;
+    const long long lo = 65536;
+    (void)dense;
     if (chunk < lo) chunk = lo;
     long long cap = (long long)(((size_t)4 << 30) / per_point) / 32 * 32;     // <= 4 GiB per buffer
     if (const char* env = std::getenv("QTET_BIG_WS_GIB")) { const double g = std::atof(env); if (g > 0) cap = (long long)(g * 0.5 * 1073741824.0 / (double)per_point) / 32 * 32; }
     if (cap < 32) cap = 32;
+    if (const char* env = std::getenv("QTET_BIG_CHUNK")) { const long long v = std::atoll(env) / 32 * 32; if (v >= 32) chunk = v; }
     if (chunk > cap) chunk = cap;
     const long long all = (B + 31) / 32 * 32;
     if (chunk > all) chunk = all;

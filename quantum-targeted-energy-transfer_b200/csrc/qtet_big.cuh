@@ -25,6 +25,8 @@ struct BigStream {
 int bigreg_padded_dim(int d);
 int bigreg_max_timesteps();
 int launch_hh_reg(const ProblemView& pv, const double* chis, int64_t n, const BigStream& bs, int sms, cudaStream_t st);
+// the same reduction with the matrix in 8 x 8 register tiles (qtet_hhfrag.cu); launch_hh_reg forwards to it unless QTET_HH_FRAG=0
+int launch_hh_frag(const ProblemView& pv, const double* chis, int64_t n, const BigStream& bs, int sms, cudaStream_t st);
 int launch_replay_reg(const ProblemView& pv, const double* chis, int64_t n, int site, const BigStream& bs,
                       const unsigned short* pair_tab, double* loss, double* grad, int32_t* tstar, double* trace, int sms,
                       cudaStream_t st, bool direct = false, int* fb_list = nullptr, int* fb_count = nullptr);

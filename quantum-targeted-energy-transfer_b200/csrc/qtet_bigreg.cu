@@ -1190,6 +1190,7 @@ int launch_replay_t(const RegArgs& a, int sms, cudaStream_t st) {
     int per_sm = 0;
     QTET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem));
     if (per_sm < 1) per_sm = 1;
+    if (const char* env = std::getenv("QTET_RP_CTAS")) { const int v = std::atoi(env); if (v > 0 && v < per_sm) per_sm = v; }
     long long grid = (long long)sms * per_sm;
     if (grid > a.n) grid = a.n;
     kern<<<(unsigned)grid, NW * 32, smem, st>>>(a);
@@ -1243,6 +1244,8 @@ static RegArgs make_args(const ProblemView& pv, const double* chis, int64_t n, i
 }
 
 int launch_hh_reg(const ProblemView& pv, const double* chis, int64_t n, const BigStream& bs, int sms, cudaStream_t st) {
+    static const bool use_frag = [] { const char* e = std::getenv("QTET_HH_FRAG"); return !(e && std::atoi(e) == 0); }();
+    if (use_frag) return launch_hh_frag(pv, chis, n, bs, sms, st);
     const RegArgs a = make_args(pv, chis, n, 0, bs, nullptr, nullptr, nullptr, nullptr, nullptr);
     switch (bigreg_padded_dim(pv.d)) {
         case 16: return launch_hh_t<16, 1, 8>(a, sms, st);

@@ -139,7 +139,8 @@ int qtet_problem_create(int max_N, int sites, const double* omegas, double coupl
     }
     // pack constants
     std::vector<double> blob;
-    auto push = [&](const std::vector<double>& v) { size_t o = blob.size(); blob.insert(blob.end(), v.begin(), v.end()); return o; };
+    // every section starts on a 16-byte boundary (the tiled Householder kernel reads the hopping rows with 16-byte loads)
+    auto push = [&](const std::vector<double>& v) { if (blob.size() & 1) blob.push_back(0.0); size_t o = blob.size(); blob.insert(blob.end(), v.begin(), v.end()); return o; };
     std::vector<double> lin(d), quad((size_t)d * sites);
     for (int m = 0; m < d; ++m) {
         double acc = 0.0;
@@ -159,6 +160,7 @@ int qtet_problem_create(int max_N, int sites, const double* omegas, double coupl
     }
     const size_t o_lin = push(lin), o_quad = push(quad), o_occ = push(p->states), o_off = push(offd),
                  o_t = push(p->tgrid), o_om = push(p->omegas);
+    if (blob.size() & 1) blob.push_back(0.0);
     const size_t o_stats = blob.size();
     blob.resize(blob.size() + 4, 0.0);            // 4 x uint64 counters (all-zero bit pattern)
     cudaError_t e = cudaMalloc(&p->dev_blob, blob.size() * sizeof(double));

@@ -25,5 +25,13 @@ names = ["hh 0 build H row", "hh 1 reduction", "hh 2 Q accumulation", "hh 3 stor
 print(f"N={N} f={len(om)} d={prob.dim} B={B} step {e0.elapsed_time(e1):.3f} ms ; CTA-cycles per point:")
 for i, n in enumerate(names):
     print(f"  {n:26s} {out[i]/B:10.1f}")
+if hasattr(_native.lib, "qtet_debug_hf_phase_cycles") or True:
+    try:
+        hf = (ctypes.c_ulonglong * 8)()
+        _native.lib.qtet_debug_hf_phase_cycles(hf, 0)
+        for i, n in enumerate(["hf 0 build H tiles", "hf 1 reduction: update (+ loop)", "hf 2 Q^T accumulation", "hf 3 store", "hf 4 red: owner (thread 0 view)", "hf 5 red: barrier 1 wait", "hf 6 red: matvec", "hf 7 red: barrier 2 wait"]):
+            print(f"  {n:26s} {hf[i]/(2*B):10.1f}   (tiled Householder kernel, both calls)")
+    except AttributeError:
+        pass
 if any(out[i] for i in range(10, 15)):       # replay statistics (only in builds that count them)
     print(f"  per point: active rounds {out[10]/B:.1f}  own-window planes {out[11]/B:.0f}  batch-window planes {out[12]/B:.0f}  trip steps {out[13]/B:.0f}  trips {out[14]/B:.1f}")
