@@ -87,7 +87,9 @@ int qtet_problem_create(int max_N, int sites, const double* omegas, double coupl
         // guard the enumeration size before doing it
         double dim = 1.0;
         for (int i = 1; i <= sites - 1; ++i) dim = dim * (max_N + i) / i;
-        if (dim > 4096) { set_error("Fock dimension too large"); return QTET_EUNSUPPORTED; }
+        // d <= 115: shared-memory / register kernels; beyond that the fused generic kernel keeps V and M in global memory, its
+        // vectors (17 d doubles per CTA) must still fit the 227 KB of shared memory
+        if (dim > 1536) { set_error("Fock dimension " + std::to_string((long long)dim) + " is too large (supported: up to 1536)"); return QTET_EUNSUPPORTED; }
         std::vector<int> cur(sites, 0);
         enumerate_states(max_N, sites, cur, 0, max_N, st);
     }
@@ -226,7 +228,7 @@ int qtet_set_path(qtet_problem* p, int path) {
     }
     if (path == QTET_PATH_GENERIC) { p->path = path; return QTET_OK; }
     if (path == QTET_PATH_SPLIT) {
-        if (!split_eligible(p->view) && !big_eligible(p->view)) { set_error("split path needs dim <= 128"); return QTET_EUNSUPPORTED; }
+        if (!split_eligible(p->view) && !big_eligible(p->view)) { set_error("the split path needs Fock dimension <= 115 (larger systems run on the generic path)"); return QTET_EUNSUPPORTED; }
         p->path = path;
         return QTET_OK;
     }

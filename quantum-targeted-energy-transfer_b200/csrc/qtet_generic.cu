@@ -12,6 +12,8 @@
 //
 // This kernel is the general/robust path (trimer, large dimers) and the on-GPU cross-check of the
 // fast split path in qtet_split.cu.
+#include <mutex>
+
 #include "qtet_common.cuh"
 #include "qtet_big.cuh"
 
@@ -41,6 +43,9 @@ struct GenericArgs {
     //         evolution + gradient as in mode 0
     int mode;
     BigStream bs;
+    // Fock dimensions whose V and M do not fit shared memory (d > 115): the two matrices live in a per-CTA slab of global
+    // memory (L1 / L2 cached) instead -- slow, but every size the reference accepts returns a result
+    double* slab = nullptr;       // [gridDim.x][2][d][ldv]
 };
 
 __device__ __forceinline__ double block_sum(double v, double* red, int tid, int nwarps) {
@@ -59,9 +64,9 @@ __global__ void generic_kernel(GenericArgs a) {
     const int d = pv.d, f = pv.f, T = pv.T, ld = a.ldv;
     const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
 
-    double* V = smem;                       // [d][ld]
+    double* V = a.slab ? a.slab + (size_t)blockIdx.x * 2 * d * ld : smem;      // [d][ld]
     double* M = V + (size_t)d * ld;         // [d][ld]
-    double* wdiag = M + (size_t)d * ld;     // [nwarps][d]
+    double* wdiag = a.slab ? smem : M + (size_t)d * ld;     // [nwarps][d]
     double* woff = wdiag + nwarps * d;      // [nwarps][d]
     double* cvec = woff + nwarps * d;       // [d]   c_i = V[0][i]
     double* zr = cvec + d;                  // [d]
@@ -460,6 +465,28 @@ size_t generic_smem_bytes(int d, int nthreads) {
     return n * sizeof(double);
 }
 
+// Per-device slab for the global-memory mode (grow-only, lives as long as the process: the launchers here have no handle
+// to hang it on, and the mode is the last-resort path of very large Fock spaces).
+static double* generic_slab(int dev, size_t bytes) {
+    static std::mutex mu;
+    static double* ptr[64] = {};
+    static size_t have[64] = {};
+    std::lock_guard<std::mutex> lock(mu);
+    dev &= 63;
+    if (bytes > have[dev]) {
+        if (ptr[dev]) { cudaDeviceSynchronize(); cudaFree(ptr[dev]); }
+        ptr[dev] = nullptr; have[dev] = 0;
+        if (cudaMalloc(&ptr[dev], bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        have[dev] = bytes;
+    }
+    return ptr[dev];
+}
+
+size_t generic_small_smem_bytes(int d, int nthreads, int T) {      // everything except V and M
+    const int nw = nthreads / 32;
+    return (2 * (size_t)nw * d + 9 * (size_t)d + (size_t)(T > 64 ? T : 64) + 32 + 2) * sizeof(double);
+}
+
 static int launch_generic_impl(const ProblemView& pv, const double* chis, int64_t B, const int* list, const int* count,
                                int site, double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st,
                                int mode = 0, const BigStream* bs = nullptr) {
@@ -471,15 +498,22 @@ static int launch_generic_impl(const ProblemView& pv, const double* chis, int64_
     QTET_CUDA(cudaGetDevice(&dev));
     QTET_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     QTET_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    bool use_slab = false;
     if (smem > (size_t)max_optin) {
-        set_error("Fock dimension " + std::to_string(pv.d) + " needs " + std::to_string(smem) +
-                  " B of shared memory per CTA; device limit is " + std::to_string(max_optin));
-        return QTET_EUNSUPPORTED;
+        // V and M move to global memory; the vectors stay in shared memory
+        smem = generic_small_smem_bytes(pv.d, nth, pv.T);
+        use_slab = true;
+        if (smem > (size_t)max_optin || mode != 0) {
+            set_error("Fock dimension " + std::to_string(pv.d) + " needs " + std::to_string(smem) +
+                      " B of shared memory per CTA even with the matrices in global memory; device limit is " + std::to_string(max_optin));
+            return QTET_EUNSUPPORTED;
+        }
     }
     QTET_CUDA(cudaFuncSetAttribute(generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     QTET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, generic_kernel, nth, smem));
     if (per_sm < 1) per_sm = 1;
+    if (use_slab && per_sm > 4) per_sm = 4;
     long long grid = (long long)sms * per_sm;     // persistent: a whole number of waves of the 148 SMs
     if (grid > B) grid = B;
     GenericArgs a;
@@ -489,6 +523,11 @@ static int launch_generic_impl(const ProblemView& pv, const double* chis, int64_
     a.mode = mode;
     if (bs) a.bs = *bs; else a.bs = BigStream{};
     if (list) { grid = 2LL * sms; if (grid > B) grid = B; }
+    if (use_slab) {
+        const size_t bytes = (size_t)grid * 2 * pv.d * a.ldv * sizeof(double);
+        a.slab = generic_slab(dev, bytes);
+        if (!a.slab) { set_error("cudaMalloc(generic-kernel slab, " + std::to_string(bytes) + " B) failed"); return QTET_ENOMEM; }
+    }
     generic_kernel<<<(unsigned)grid, nth, smem, st>>>(a);
     count_launch();
     QTET_CUDA(cudaGetLastError());

@@ -326,8 +326,9 @@ print('ok')
 
 
 def test_large_dimension_limits(native, O):
-    """d = 115 (dimer N = 114) is the largest Fock space whose V and K fit shared memory; beyond it the library
-    refuses loudly instead of silently doing something else."""
+    """d = 115 (dimer N = 114) is the largest Fock space whose V and K fit shared memory.  Beyond it the fused generic
+    kernel keeps the two matrices in a global-memory slab (the reference has no size limit, HamiltonianLoss.py:39-47):
+    trimer N = 14 (d = 120, dense H) and dimer N = 128 (d = 129) must return the oracle's numbers, not an error."""
     c = make_const(114)
     X = np.array([[0.05, -0.05], [1.0, 2.0]])
     p = native.Problem.from_const(c)
@@ -336,10 +337,17 @@ def test_large_dimension_limits(native, O):
     Lr, gr, kr = O.loss_grad_batch(c, X, 1)
     assert np.abs(L - Lr).max() < 5e-9 and (k == kr).all()
     p.close()
-    big = native.Problem.from_const(make_const(130))
-    with pytest.raises(native.QtetError, match="shared memory"):
-        big.loss_grad(np.array([[0.1, -0.1]]))
-    big.close()
+    rng = np.random.default_rng(11)
+    for N, omegas in [(128, (-3, 3)), (14, (-3, 3, 3))]:
+        c = make_const(N, omegas)
+        f = len(omegas)
+        X = np.concatenate([rng.uniform(-2.0, 2.0, (7, f)), np.array([[6.0 / N, -6.0 / N] + [0.0] * (f - 2)])])
+        p = native.Problem.from_const(c)
+        assert p.dim > 115 and p.get_path() == native.QTET_PATH_GENERIC
+        p.close()
+        _compare(native, O, c, X, f - 1, loss_atol=2e-9, grad_rtol=2e-6)      # tolerances of test_dimer_large_fock_space
+    with pytest.raises(native.QtetError, match="too large"):
+        native.Problem.from_const(make_const(60, (-3, 3, 3)))     # d = 1891
 
 
 @pytest.mark.parametrize("N,omegas,coupling,max_t,timesteps", [
