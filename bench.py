@@ -229,9 +229,13 @@ def run_reference_arm(args, w, const):
 
 
 def measure_secondary(_native, torch, dev, local, flush, peak, name="trimer10", steps=3, warmup=3):
+    """The second system BASELINE.json's metric names (trimer N=10, dense H, large-d path), measured beside the headline with
+    the same rules: inputs resident + CUDA events + L2 flush for `value`, host buffers through qtet_loss_grad_host for `e2e`,
+    per-kernel event times and the ncu-measured DRAM traffic for its own roofline block."""
     w = WORKLOADS[name]
     const = make_const(w)
     prob = _native.Problem.from_const(const, device=local)
+    path_name = _native.PATH_NAMES[prob.get_path()]
     pts = make_points(w)
     B, f = pts.shape
     chis = torch.from_numpy(pts).to(dev)
@@ -251,10 +255,53 @@ def measure_secondary(_native, torch, dev, local, flush, peak, name="trimer10", 
     d = prob.dim
     F = algorithmic_flops(d, const["timesteps"], tridiagonal=(f == 2))
     rate = B / (ms * 1e-3)
+    # end to end with pinned host buffers (H2D + kernels + D2H inside the call)
+    h_chis = torch.from_numpy(pts).pin_memory()
+    h_loss = torch.empty(B, dtype=torch.float64).pin_memory()
+    h_grad = torch.empty(B, f, dtype=torch.float64).pin_memory()
+    h_ts = torch.empty(B, dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        rc = _native.lib.qtet_loss_grad_host(prob._h, h_chis.data_ptr(), B, f - 1, h_loss.data_ptr(), h_grad.data_ptr(), h_ts.data_ptr())
+        if rc:
+            raise RuntimeError(_native.lib.qtet_last_error().decode())
+
+    e2e_step(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_rate = B * steps / (time.perf_counter() - t0)
+    # seeded sample of the returned losses against the oracle
+    idx = checksum_sample_indices(B, 512)
+    from oracle import qtet_oracle as _O
+    L_ref = _O.loss_grad_batch(const, pts[idx], f - 1)[0]
+    diff = float(np.abs(h_loss.numpy()[idx] - L_ref).max())
+    kms = {k: v for k, v in kern.items() if v[1] > 0}
+    tot = sum(v[0] for v in kms.values()) or 1.0
+    kernels = {k: {"launches": v[1], "ms_per_launch": v[0] / v[1], "points_per_launch": v[2] / v[1], "share_of_kernel_time": v[0] / tot}
+               for k, v in kms.items()}
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            tj = json.load(fh)
+        for k in kms:
+            e = tj.get(f"{name}/{path_name}/{k}")
+            if e:
+                traffic[k] = {"dram_bytes_per_point": e["dram_bytes_per_point"], "source": e["source"]}
+    except Exception:
+        pass
+    dom = max(kms, key=lambda k: kms[k][0]) if kms else None
     res = {"workload": w["label"], "value": rate, "unit": "evals/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
-           "fock_dim": d, "flops_per_eval": F, "achieved_tflops": rate * F / 1e12,
+           "fock_dim": d, "flops_per_eval": F, "achieved_tflops": rate * F / 1e12, "kernel_path": path_name,
            "roofline_frac": (rate * F / 1e12 / peak) if peak else None,
-           "kernels_ms_per_step": {k: v[0] / steps for k, v in kern.items() if v[1] > 0}}
+           "roofline": {"bound": "fp64", "peak": peak, "unit": "TFLOP/s", "kernel": dom, "kernels": kernels, "traffic_per_point": traffic,
+                        "whole_step": {"achieved": rate * F / 1e12, "frac": (rate * F / 1e12 / peak) if peak else None},
+                        "hbm_algorithmic_bytes_per_eval": 8 * f + 8 * (1 + f) + 4},
+           "e2e": {"value": e2e_rate, "unit": "evals/s", "h2d_bytes_per_step": int(B * f * 8), "d2h_bytes_per_step": int(B * (8 + 8 * f + 4)),
+                   "checksum_check": {"points": int(len(idx)), "max_abs_diff": diff, "tolerance": 1e-10 * const["max_N"],
+                                      "ok": bool(diff <= 1e-10 * const["max_N"])}},
+           "kernels_ms_per_step": {k: v[0] / steps for k, v in kms.items()}, "kernel_stats": prob.stats()}
     prob.close()
     return res
 

@@ -727,7 +727,7 @@ bool big_direct_eligible(const ProblemView& pv) {
 
 static long long big_direct_chunk(const ProblemView& pv, long long B) {
     const bool dense = !pv.tridiag;
-    const size_t per_point = (size_t)pv.d * 8 * (dense ? 4 : 2) + 4 + (dense ? (size_t)pv.d * pv.d * 8 : 0);
+    const size_t per_point = (size_t)pv.d * 8 * (dense ? 4 : 2) + 4 + (dense ? (size_t)pv.d * pv.d * 8 + hh_frag_scratch_bytes(pv.d) : 0);
     // Four chunks per call, but never fewer than 65536 points: the eigenvalue kernel is one thread per point and a pure latency
     // chain -- with 16384 points it runs 3.5 warps per SM and takes as long as with 65536 (measured: trimer N=10, 4 x 0.84 ms
     // against 1 x 2.0 ms per 65536 points), and the kernels of consecutive chunks do not overlap anyway (each fills the machine).
@@ -784,7 +784,9 @@ int launch_big_direct(const ProblemView& pv, BigWorkspace** wsp, const double* c
     const size_t o_trid = o_list + align((size_t)chunk * 4);
     const size_t o_trie = o_trid + (dense ? align((size_t)chunk * d * 8) : 0);
     const size_t o_q = o_trie + (dense ? align((size_t)chunk * d * 8) : 0);
-    const size_t buf_bytes = o_q + (dense ? align((size_t)chunk * d * d * 8) : 0);
+    const size_t o_rfl = o_q + (dense ? align((size_t)chunk * d * d * 8) : 0);
+    const size_t rfl_pp = dense ? hh_frag_scratch_bytes(d) : 0;
+    const size_t buf_bytes = o_rfl + align((size_t)chunk * rfl_pp);
     if (2 * buf_bytes > ws->blob_bytes) {
         if (ws->blob) { cudaDeviceSynchronize(); cudaFree(ws->blob); }
         ws->blob = nullptr; ws->blob_bytes = 0;
@@ -818,6 +820,7 @@ int launch_big_direct(const ProblemView& pv, BigWorkspace** wsp, const double* c
         bs.ev = (double*)base; bs.adiag = (double*)(base + o_ad);
         bs.capit = 0; bs.maxr = ws->maxr;
         if (dense) { bs.tri_d = (double*)(base + o_trid); bs.tri_e = (double*)(base + o_trie); bs.qmat = (double*)(base + o_q); }
+        if (rfl_pp) bs.rfl = (double*)(base + o_rfl);
         int* fb_list = (int*)(base + o_list);
         int* fb_count = ws->fb_count + buf;
         const double* cchis = chis + lo * pv.f;

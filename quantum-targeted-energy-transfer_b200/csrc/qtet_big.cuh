@@ -19,6 +19,8 @@ struct BigStream {
     double* qmat = nullptr;        // [n][d][d]
     // direct path (eigenvectors by two-sided recurrences): written by the eigenvalue-only QL kernel
     double* adiag = nullptr;       // [n][d]           diagonal of the (Householder-reduced) tridiagonal minus its mean
+    // staged Householder reduction (qtet_hhfrag.cu): reflectors of the first stage, hh_frag_scratch_bytes(d) per point (or null)
+    double* rfl = nullptr;
 };
 
 // register-resident kernels (qtet_bigreg.cu); they store / expect Q column-major
@@ -27,6 +29,7 @@ int bigreg_max_timesteps();
 int launch_hh_reg(const ProblemView& pv, const double* chis, int64_t n, const BigStream& bs, int sms, cudaStream_t st);
 // the same reduction with the matrix in 8 x 8 register tiles (qtet_hhfrag.cu); launch_hh_reg forwards to it unless QTET_HH_FRAG=0
 int launch_hh_frag(const ProblemView& pv, const double* chis, int64_t n, const BigStream& bs, int sms, cudaStream_t st);
+size_t hh_frag_scratch_bytes(int d);
 int launch_replay_reg(const ProblemView& pv, const double* chis, int64_t n, int site, const BigStream& bs,
                       const unsigned short* pair_tab, double* loss, double* grad, int32_t* tstar, double* trace, int sms,
                       cudaStream_t st, bool direct = false, int* fb_list = nullptr, int* fb_count = nullptr);

@@ -82,7 +82,20 @@ struct HfArgs {
     const double* chis;
     long long n;
     double* tri_d; double* tri_e; double* qmat;
+    // staged reduction (see MODE below)
+    int koff = 0;                 // first row / column of the trailing block the stage works on
+    double* rfl = nullptr;        // [n][koff][DP + 1]  reflectors 0 .. koff-1 of stage A (+ beta in the last entry of the row)
 };
+
+// Stage sizes.  The reduction is a latency chain per column whatever the number of live tiles, so its throughput is the number
+// of matrices resident per SM: 4 at d = 66 (108 registers of matrix per lane).  Once 8 (MT - 6) columns are done the live
+// block fits the 48-wide kernel (72 registers of matrix, two warps): the rest of the reduction AND the accumulation of its
+// part of Q run there with one warp per point and 10 CTAs per SM.
+//   MODE 0  everything in one kernel (any size)
+//   MODE 1  stage A: build H, columns 0 .. koff-1, then hand over: trailing block -> scratch (the point's Q slot), reflectors -> rfl
+//   MODE 2  stage B (48-wide kernel): the trailing block as its whole problem; X_B = Q_B^T lands in the trailing block of the Q slot
+//   MODE 3  stage C: X = (I + X_B) H_{koff-1} ... H_0 with the reflectors of stage A, Q stored
+constexpr int kStageD = 48;
 
 template <int D, int NW>
 struct HfLayout {
@@ -107,13 +120,17 @@ constexpr int reg_cap(int nw, int minb) {
 }
 
 // PIPE: the one-barrier-per-column reduction (see the comment at its top), otherwise the plain two-barrier one.
-template <int D, int NW, int MINB, bool PIPE>
+template <int D, int NW, int MINB, bool PIPE, int MODE = 0>
 __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) hh_frag_kernel(HfArgs a_) {
     using L = HfLayout<D, NW>;
     constexpr int MT = L::MT, DP = L::DP, SL = L::SL, NT = NW * 32;
     extern __shared__ __align__(16) double sm[];
     const ProblemView& pv = a_.pv;
-    const int d = pv.d, f = pv.f;
+    const int dfull = pv.d, f = pv.f;
+    const int koff = (MODE == 0) ? 0 : a_.koff;
+    const int d = (MODE == 2) ? dfull - koff : dfull;          // the dimension this kernel's index logic sees
+    constexpr int KBS = (MT > kStageD / 8) ? MT - kStageD / 8 : 0;   // MODE 1 / 3: blocks of eight columns done by stage A
+    static_assert(!PIPE || MODE == 0, "the staged reduction uses the two-barrier column step");
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // tells the compiler the warp index is warp-uniform: branches on it
     const int lg = lane >> 2, lt = lane & 3;                     // need no convergence bookkeeping around the shuffles inside
@@ -133,9 +150,10 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) hh_fra
         __syncthreads();                                 // the previous point is done with every shared region
         HPHASE_DECL();
         HPHASE_START();
+        double2 a[SL][MT];
+        if constexpr (MODE == 0 || MODE == 1) {
         // ---- my tiles of H.  The hopping part is the same for every point (L1-resident after the first one): all loads are
         // issued unconditionally from clamped addresses, the masks and the diagonal follow.
-        double2 a[SL][MT];
 #pragma unroll
         for (int j = 0; j < SL; ++j) {
             const int r = 8 * (warp + NW * j) + lg;
@@ -165,6 +183,21 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) hh_fra
                 if (c0 == r) x = dg;
                 if (c0 + 1 == r) y = dg;
                 a[j][nt] = make_double2(x, y);
+            }
+        }
+        } else if constexpr (MODE == 2) {
+            // the trailing block stage A left in the point's Q slot: [kStageD][kStageD], zero padded
+            const double* tm = a_.qmat + (size_t)b * dfull * dfull;
+#pragma unroll
+            for (int j = 0; j < SL; ++j) {
+                const int r = 8 * (warp + NW * j) + lg;
+#pragma unroll
+                for (int nt = 0; nt < MT; ++nt) {
+                    const int c0 = 8 * nt + 2 * lt;
+                    const bool in = (r < kStageD) && (c0 + 1 < kStageD);
+                    a[j][nt].x = in ? tm[r * kStageD + c0] : 0.0;
+                    a[j][nt].y = in ? tm[r * kStageD + c0 + 1] : 0.0;
+                }
             }
         }
         HPHASE_MARK(0);
@@ -349,6 +382,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) hh_fra
             constexpr int kb = decltype(KBc)::value;
             constexpr int wk = kb % NW, jk = kb / NW;     // warp / slot that own rows 8 kb .. 8 kb + 7
             constexpr int q0 = kb / NW, r0 = kb % NW;     // live slots: j >= q0 (warps >= r0), j >= q0 + 1 (warps < r0)
+            if constexpr (MODE != 3 && (MODE != 1 || kb < KBS))
             if (8 * kb < d - 2) {
                 const bool lowj = (warp >= r0);
 #pragma unroll 1
@@ -481,6 +515,34 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) hh_fra
         });
         }
         HPHASE_MARK(1);
+        if constexpr (MODE == 1) {
+            // ---- stage A hands over: tridiagonal entries of its columns, reflectors (+ beta), trailing block
+            __syncthreads();
+            for (int i = tid; i < koff; i += NT) {
+                a_.tri_d[(size_t)b * d + i] = s_diag[i];
+                a_.tri_e[(size_t)b * d + i] = s_off[i];
+            }
+            {
+                double* rf = a_.rfl + (size_t)b * koff * (DP + 1);
+                for (int i = tid; i < koff * (DP + 1); i += NT) {
+                    const int k = i / (DP + 1), c = i - k * (DP + 1);
+                    rf[i] = (c < DP) ? refl[(size_t)(k + 1) * DP + c] : s_beta[k];      // (reflector k sits in row k + 1 of the buffer)
+                }
+                double* tm = a_.qmat + (size_t)b * d * d;
+#pragma unroll
+                for (int j = 0; j < SL; ++j) {
+                    const int r = 8 * (warp + NW * j) + lg - 8 * KBS;
+#pragma unroll
+                    for (int nt = KBS; nt < MT; ++nt) {
+                        const int c0 = 8 * (nt - KBS) + 2 * lt;
+                        if (r >= 0 && r < kStageD) { tm[r * kStageD + c0] = a[j][nt].x; tm[r * kStageD + c0 + 1] = a[j][nt].y; }
+                    }
+                }
+            }
+            HPHASE_MARK(3);
+            continue;
+        }
+        if constexpr (MODE == 0 || MODE == 2) {
         // ---- the last 2 x 2 block (rows d-2, d-1)
 #pragma unroll
         for (int j = 0; j < SL; ++j) {
@@ -501,8 +563,9 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) hh_fra
         if (tid == 0) s_off[d - 1] = 0.0;
         __syncthreads();
         for (int i = tid; i < d; i += NT) {
-            a_.tri_d[(size_t)b * d + i] = s_diag[i];
-            a_.tri_e[(size_t)b * d + i] = s_off[i];
+            a_.tri_d[(size_t)b * dfull + koff + i] = s_diag[i];
+            a_.tri_e[(size_t)b * dfull + koff + i] = s_off[i];
+        }
         }
 
         // ---- X = Q^T = H_{d-3} ... H_0, accumulated backwards (no barrier: the reflectors are all in shared memory)
@@ -515,9 +578,35 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) hh_fra
                 a[j][nt] = make_double2((c0 == r) ? 1.0 : 0.0, (c0 + 1 == r) ? 1.0 : 0.0);
             }
         }
+        if constexpr (MODE == 3) {
+            // reflectors of stage A back into shared memory, X_B (stage B) into the trailing block of X
+            const double* rf = a_.rfl + (size_t)b * koff * (DP + 1);
+            for (int i = tid; i < koff * (DP + 1); i += NT) {
+                const int k = i / (DP + 1), c = i - k * (DP + 1);
+                if (c < DP) refl[(size_t)(k + 1) * DP + c] = rf[i]; else s_beta[k] = rf[i];
+            }
+            const double* q = a_.qmat + (size_t)b * d * d;
+#pragma unroll
+            for (int j = 0; j < SL; ++j) {
+                const int r = 8 * (warp + NW * j) + lg;
+#pragma unroll
+                for (int nt = KBS; nt < MT; ++nt) {
+                    const int c0 = 8 * nt + 2 * lt;
+                    // unconditional loads from clamped addresses (they all issue at once), then the masks
+                    const int rc = (r >= koff && r < d) ? r : koff;
+                    const double x = __ldg(q + (size_t)rc * d + (c0 < d ? c0 : koff)), y = __ldg(q + (size_t)rc * d + (c0 + 1 < d ? c0 + 1 : koff));
+                    if (r >= koff && r < d) {
+                        if (c0 < d) a[j][nt].x = x;
+                        if (c0 + 1 < d) a[j][nt].y = y;
+                    }
+                }
+            }
+            __syncthreads();
+        }
         static_for<MT>([&](auto KBc) {
             constexpr int kb = MT - 1 - decltype(KBc)::value;
             constexpr int q0 = kb / NW, r0 = kb % NW;
+            if constexpr (MODE != 3 || kb < KBS)
             if (8 * kb < d - 2) {
                 const bool lowj = (warp >= r0);
 #pragma unroll 1
@@ -562,9 +651,12 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) hh_fra
             }
         });
         HPHASE_MARK(2);
-        // ---- Q column-major = X row-major: the column pair of a lane is contiguous
+        // ---- Q column-major = X row-major: the column pair of a lane is contiguous  (stage B: into the trailing block)
         {
-            double* q = a_.qmat + (size_t)b * d * d;
+            const int soff = (MODE == 2) ? koff : 0;         // stage B writes the trailing block, everybody else the whole matrix
+            double* q = a_.qmat + (size_t)b * dfull * dfull + (size_t)soff * dfull + soff;
+            const bool vec = ((dfull | soff) & 1) == 0;
+            if constexpr (MODE == 2) __syncthreads();        // every thread has read the trailing block that lives in this slot
 #pragma unroll
             for (int j = 0; j < SL; ++j) {
                 const int r = 8 * (warp + NW * j) + lg;
@@ -572,11 +664,11 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) hh_fra
 #pragma unroll
                     for (int nt = 0; nt < MT; ++nt) {
                         const int c0 = 8 * nt + 2 * lt;
-                        if (even_d && c0 + 1 < d) {
-                            *reinterpret_cast<double2*>(q + (size_t)r * d + c0) = a[j][nt];
+                        if (vec && c0 + 1 < d) {
+                            *reinterpret_cast<double2*>(q + (size_t)r * dfull + c0) = a[j][nt];
                         } else {
-                            if (c0 < d) q[(size_t)r * d + c0] = a[j][nt].x;
-                            if (c0 + 1 < d) q[(size_t)r * d + c0 + 1] = a[j][nt].y;
+                            if (c0 < d) q[(size_t)r * dfull + c0] = a[j][nt].x;
+                            if (c0 + 1 < d) q[(size_t)r * dfull + c0 + 1] = a[j][nt].y;
                         }
                     }
                 }
@@ -586,10 +678,10 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) hh_fra
     }
 }
 
-template <int D, int NW, int MINB, bool PIPE>
+template <int D, int NW, int MINB, bool PIPE, int MODE = 0>
 int launch_hf_t(const HfArgs& a, int sms, cudaStream_t st) {
     const size_t smem = (size_t)HfLayout<D, NW>::TOTAL * sizeof(double);
-    auto kern = hh_frag_kernel<D, NW, MINB, PIPE>;
+    auto kern = hh_frag_kernel<D, NW, MINB, PIPE, MODE>;
     static int per_sm_cached[64] = {};               // per instantiation and device: the function attributes are set once
     int dev = 0;
     QTET_CUDA(cudaGetDevice(&dev));
@@ -621,9 +713,40 @@ extern "C" void qtet_debug_hf_phase_cycles(unsigned long long* out, int reset) {
 }
 #endif
 
+// Stage A / B / C of the staged reduction (see MODE at the top): the wide kernel for the first koff columns, the 48-wide one for
+// the rest of the reduction and its part of Q, the wide one again for the reflectors of stage A.
+template <int D, int NW, int MINB>
+int launch_hf_staged(HfArgs a, int sms, cudaStream_t st) {
+    a.koff = 8 * (HfLayout<D, NW>::MT - kStageD / 8);
+    int rc = launch_hf_t<D, NW, MINB, false, 1>(a, sms, st);
+    if (rc) return rc;
+    // stage B with ONE warp per point (six row tiles per lane, 10 CTAs per SM): no cross-warp sums, cheap barriers.  Measured on
+    // the trimer N=10 (whole Householder stage per 65536 points): 10.1 ms, against 10.8 ms with two warps x 8 CTAs and x 6 CTAs.
+    rc = launch_hf_t<kStageD, 1, 10, false, 2>(a, sms, st);
+    if (rc) return rc;
+    return launch_hf_t<D, NW, MINB, false, 3>(a, sms, st);
+}
+
+// bytes of hand-over scratch (reflectors of stage A) per point, 0 when the dimension is reduced in one kernel
+size_t hh_frag_scratch_bytes(int d) {
+    const int D = bigreg_padded_dim(d);
+    if (D <= kStageD) return 0;
+    const int MT = (D + 7) / 8, koff = 8 * (MT - kStageD / 8);
+    return (size_t)koff * (8 * MT + 1) * sizeof(double);
+}
+
 int launch_hh_frag(const ProblemView& pv, const double* chis, int64_t n, const BigStream& bs, int sms, cudaStream_t st) {
     HfArgs a;
-    a.pv = pv; a.chis = chis; a.n = n; a.tri_d = bs.tri_d; a.tri_e = bs.tri_e; a.qmat = bs.qmat;
+    a.pv = pv; a.chis = chis; a.n = n; a.tri_d = bs.tri_d; a.tri_e = bs.tri_e; a.qmat = bs.qmat; a.rfl = bs.rfl;
+    static const bool staged_on = [] { const char* e = std::getenv("QTET_HH_STAGED"); return !(e && std::atoi(e) == 0); }();
+    if (staged_on && bs.rfl != nullptr) {
+        switch (bigreg_padded_dim(pv.d)) {
+            case 66: return launch_hf_staged<66, 3, 4>(a, sms, st);
+            case 84: return launch_hf_staged<84, 3, 2>(a, sms, st);
+            case 101: return launch_hf_staged<101, 4, 2>(a, sms, st);
+            default: break;
+        }
+    }
     // QTET_HH_FRAG=2 selects the one-barrier (pipelined) reduction: correct, but measured SLOWER (trimer N=10: 22.7 ms against 13.0 ms
     // per 65536 points -- its longer straight-line body stalls on instruction fetch, 17 % no_instruction, and spills)
     static const bool pipe = [] { const char* e = std::getenv("QTET_HH_FRAG"); return e && std::atoi(e) == 2; }();
@@ -641,3 +764,16 @@ int launch_hh_frag(const ProblemView& pv, const double* chis, int64_t n, const B
 }
 
 }  // namespace qtet
+
+#ifdef QTET_DEBUG_EXPORTS
+// debug builds only: run the Householder stage alone on caller-provided device buffers (tools/debug_hh.py)
+extern "C" int qtet_debug_hh(const qtet_problem* p, const double* chis, long long n, double* tri_d, double* tri_e, double* qmat, double* rfl) {
+    qtet::BigStream bs;
+    bs.tri_d = tri_d; bs.tri_e = tri_e; bs.qmat = qmat; bs.rfl = rfl;
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+    const int rc = qtet::launch_hh_frag(p->view, chis, n, bs, sms, 0);
+    cudaDeviceSynchronize();
+    return rc;
+}
+#endif
