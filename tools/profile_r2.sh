@@ -16,24 +16,28 @@ for w in dimer20 trimer10 dimer100; do
   python tools/ncu_summary.py $O/${TAG}_launches_$w.csv > $O/${TAG}_launches_${w}_summary.txt
 done
 fi
-cap() {  # cap <workload> <kernel regex> <skip> <object> <name> <points per launch>
-  $NCU --set full --import-source on -k regex:$2 --launch-skip $3 --launch-count 1 -f -o /tmp/${TAG}_$5 python tools/ncu_target.py $1 > $O/${TAG}_ncu_$5.log 2>&1
-  python tools/ncu_metrics_md.py /tmp/${TAG}_$5.ncu-rep "$1: $2 (ncu --set full, one launch, $6 points)" $6 > $O/${TAG}_metrics_$5.md 2>> $O/${TAG}_ncu_$5.log
-  python tools/ncu_stalls.py /tmp/${TAG}_$5.ncu-rep $B/$4 $2 > $O/${TAG}_stalls_$5.md 2>> $O/${TAG}_ncu_$5.log
+cap() {  # cap <workload> <points> <ncu kernel regex> <launch skip> <object> <mangled-name fragment> <capture name>
+  $NCU --set full --import-source on -k regex:$3 --launch-skip $4 --launch-count 1 -f -o /tmp/${TAG}_$7 python tools/ncu_target.py $1 $2 > $O/${TAG}_ncu_$7.log 2>&1
+  python tools/ncu_metrics_md.py /tmp/${TAG}_$7.ncu-rep "$1: $3 (ncu --set full --clock-control none, one launch of tools/ncu_target.py $1 $2, $2 points)" $2 > $O/${TAG}_metrics_$7.md 2>> $O/${TAG}_ncu_$7.log
+  python tools/ncu_stalls.py /tmp/${TAG}_$7.ncu-rep $B/$5 $6 > $O/${TAG}_stalls_$7.md 2>> $O/${TAG}_ncu_$7.log
 }
 if [ "$WHAT" = all ] || [ "$WHAT" = full ]; then
-python tools/ncu_target.py dimer20 > $O/${TAG}_target_dimer20.log 2>&1 && {
-  cap dimer20 direct_kernel 4 qtet_direct.o dimer20_kd 65536
-  cap dimer20 eig_scalar_kernel 4 qtet_direct.o dimer20_ke 65536
+python tools/ncu_target.py dimer20 65536 > $O/${TAG}_target_dimer20.log 2>&1 && {
+  # 65536 points = one chunk per pass: K_E, K_D, fallback list; the second pass is captured
+  cap dimer20 65536 direct_kernel 1 qtet_direct.o direct_kernelILi21ELi8ELi2ELi4ELb1 dimer20_kd
+  cap dimer20 65536 eig_scalar_kernel 1 qtet_direct.o eig_scalar_kernel dimer20_ke
 }
-python tools/ncu_target.py trimer10 > $O/${TAG}_target_trimer10.log 2>&1 && {
-  cap trimer10 hh_reg_kernel 1 qtet_bigreg.o trimer10_hh 16384
-  cap trimer10 eig_scalar_big 1 qtet_big.o trimer10_eig 16384
-  cap trimer10 replay_reg_kernel 1 qtet_bigreg.o trimer10_replay 16384
+python tools/ncu_target.py trimer10 65536 > $O/${TAG}_target_trimer10.log 2>&1 && {
+  # one chunk per pass: Householder stages A, B, C, eigenvalues, eigenvectors + evolution + gradient
+  cap trimer10 65536 hh_frag_kernel 3 qtet_hhfrag.o hh_frag_kernelILi66ELi3ELi4ELb0ELi1 trimer10_hhA
+  cap trimer10 65536 hh_frag_kernel 4 qtet_hhfrag.o hh_frag_kernelILi48ELi1ELi10ELb0ELi2 trimer10_hhB
+  cap trimer10 65536 hh_frag_kernel 5 qtet_hhfrag.o hh_frag_kernelILi66ELi3ELi4ELb0ELi3 trimer10_hhC
+  cap trimer10 65536 eig_scalar_big 1 qtet_big.o eig_scalar_big_kernelILb1 trimer10_eig
+  cap trimer10 65536 replay_reg_kernel 1 qtet_bigreg.o replay_reg_kernelILi66ELi3ELi4ELi4ELb1 trimer10_replay
 }
-python tools/ncu_target.py dimer100 > $O/${TAG}_target_dimer100.log 2>&1 && {
-  cap dimer100 replay_reg_kernel 1 qtet_bigreg.o dimer100_replay 16384
-  cap dimer100 eig_scalar_big 1 qtet_big.o dimer100_eig 16384
+python tools/ncu_target.py dimer100 65536 > $O/${TAG}_target_dimer100.log 2>&1 && {
+  cap dimer100 65536 replay_reg_kernel 1 qtet_bigreg.o replay_reg_kernelILi101ELi4ELi2ELi2ELb1 dimer100_replay
+  cap dimer100 65536 eig_scalar_big 1 qtet_big.o eig_scalar_big_kernelILb1 dimer100_eig
 }
 fi
-ls -la $O | tail -40
+ls -la $O | tail -50
