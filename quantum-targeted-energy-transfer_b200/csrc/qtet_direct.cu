@@ -35,7 +35,13 @@ constexpr int kWarpsE = 4;                              // warps per CTA, eigenv
 constexpr double kGapGS = 2.44140625e-4;                // 2^-12: re-orthogonalise neighbours closer than this (x ||T||)
 constexpr double kGapFB = 5.820766091346741e-11;        // 2^-34: numerically degenerate -> generic kernel
 constexpr int kMaxF = 8;
-constexpr double kCsig = 1e-19;                         // eigenvectors with |c_i| below this carry no weight in psi(t)
+#ifndef QTET_CSIG
+#define QTET_CSIG 1e-14
+#endif
+// Eigenvectors with |c_i| = |V[0][i]| below this carry no weight in psi(t) and are left out of the evolution: dropping them
+// moves psi by at most d * 1e-14 and <n(t)> by at most 2 N d 1e-14 (8e-12 at N = 20, 2e-11 at N = 31) -- two orders below the
+// 1e-10 N parity tolerance.  On the config-2 grid 11.7 of the 21 columns survive on average (14.4 with 1e-19).
+constexpr double kCsig = QTET_CSIG;
 
 // Shifted diagonal of H.  The two kernels must see bit-identical values, hence explicit fma / no contraction freedom:
 // a_m = lin_m + sum_k chi_k quad_mk  (HamiltonianLoss.py:131-134 with lin = sum_k omega_k n_k, quad = n_k^2 / 2).
@@ -773,6 +779,20 @@ void direct_workspace_free(DirectWorkspace* ws) {
 int launch_generic_list(const ProblemView& pv, const double* chis, const int* list, const int* count, long long max_count,
                         int site, double* loss, double* grad, int32_t* tstar, double* trace, cudaStream_t st);
 
+// eig_scalar_kernel is ONE function shared by handles of every Fock dimension: its dynamic shared-memory limit only ever grows
+// (a handle of a smaller system created later must not lower it under the feet of an older, larger one).
+static int raise_eig_smem_limit(size_t bytes) {
+    static size_t have[64] = {};
+    int dev = 0;
+    QTET_CUDA(cudaGetDevice(&dev));
+    dev &= 63;
+    if (bytes > have[dev]) {
+        QTET_CUDA(cudaFuncSetAttribute(eig_scalar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        have[dev] = bytes;
+    }
+    return QTET_OK;
+}
+
 static int direct_workspace_init(const ProblemView& pv, DirectWorkspace** wsp) {
     if (*wsp) return QTET_OK;
     DirectWorkspace* ws = new DirectWorkspace();
@@ -796,7 +816,7 @@ static int direct_workspace_init(const ProblemView& pv, DirectWorkspace** wsp) {
     }
     if (rc) return rc;
     ws->smem_e = (size_t)kWarpsE * 2 * pv.d * 32 * sizeof(double);
-    QTET_CUDA(cudaFuncSetAttribute(eig_scalar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws->smem_e));
+    { const int rc_e = raise_eig_smem_limit(ws->smem_e); if (rc_e) return rc_e; }
     QTET_CUDA(cudaFuncSetAttribute(eig_scalar_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     QTET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ws->per_sm_e, eig_scalar_kernel, kWarpsE * 32, ws->smem_e));
     if (ws->per_sm_e < 1) ws->per_sm_e = 1;

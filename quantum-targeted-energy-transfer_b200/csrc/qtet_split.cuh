@@ -145,8 +145,8 @@ struct BLayout {
 //
 // PERM (direct path): the eigen-indices arrive sorted by |c_i| descending, `evs` [D] holds the eigenvalues of this point
 // in that order (shared memory) and only the first `ncol` (warp-uniform) columns carry weight in psi(t) = V (c . z(t)):
-// c_i = V[0][i] is the overlap of eigenvector i with the initial state, and with |c_i| <= 1e-19 a column cannot move
-// <n(t)> by more than 1e-18 N.  On the config-2 grid 13 of the 21 columns survive on average.  The gradient still needs
+// c_i = V[0][i] is the overlap of eigenvector i with the initial state, and with |c_i| <= kCsig (1e-14, qtet_direct.cu) a column
+// cannot move <n(t)> by more than 2e-14 N.  On the config-2 grid 11.7 of the 21 columns survive on average.  The gradient still needs
 // every column (a = V^T w is not small for those i).  `nsig` is the point's own count: its c_i beyond that are set to
 // exactly 0, so that a point's result is bit-identical whatever the other points of the warp need (batch invariance).
 template <int D, int G, bool PERM = false>
@@ -234,7 +234,7 @@ __device__ __forceinline__ void evolve_and_grad(const SplitArgs& a, double (&v)[
             columns(std::integral_constant<int, D>{});
         }
 #else
-        // columns in groups of four with ONE warp-uniform exit test per group (PERM: the columns from ncol on have |c_i| <= 1e-19
+        // columns in groups of four with ONE warp-uniform exit test per group (PERM: the columns from ncol on have |c_i| <= kCsig
         // and z_i = 0): inside a group the loads run ahead of the FMAs, a test per column would serialise them
 #pragma unroll
         for (int i0 = 0; i0 < D; i0 += QTET_EVO_GROUP) {

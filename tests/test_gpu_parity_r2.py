@@ -278,3 +278,19 @@ def test_reference_style_per_guess_loop_shares_one_handle(native):
     opt(0.5, -0.5)
     handles.add(id(opt._ensure_loss().problem))
     assert len(handles) == 1
+
+
+def test_handles_of_different_sizes_interleaved(native, O):
+    """Kernels shared by every Fock dimension (the thread-per-point eigenvalue kernels) keep ONE dynamic shared-memory limit per
+    device: a handle for a small system created later must not lower it for an older, larger one (regression: 'invalid
+    argument' from the eigenvalue launch of the older handle)."""
+    big, X = native.Problem.from_const(make_const(20)), np.array([[1.5, -1.5], [0.3, -0.3]])
+    L0 = big.loss_grad(X)[0].cpu().numpy()
+    for N in (2, 31, 3):
+        small = native.Problem.from_const(make_const(N))
+        small.loss_grad(X)
+        L1 = big.loss_grad(X)[0].cpu().numpy()
+        assert np.array_equal(L0, L1)
+        small.close()
+    assert np.abs(L0 - O.loss_grad_batch(make_const(20), X, 1)[0]).max() < 1e-10 * 20
+    big.close()
