@@ -434,6 +434,9 @@ constexpr double kGapGS = 2.44140625e-4;                // 2^-12: re-orthogonali
 constexpr double kGapFB = 5.820766091346741e-11;        // 2^-34: numerically degenerate -> generic kernel
 constexpr double kRecBig = 1.6069380442589903e60;       // 2^200
 constexpr double kRecF = 8.636168555094445e-78;         // 2^-256
+constexpr double kCsigBig = 1e-14;                      // eigenvectors with |c_i| below this are left out of the time evolution
+constexpr double kCsigGrad = 1e-18;                     // ... and index pairs whose c_i, c_j are BOTH below this out of the gradient kernel
+constexpr int kWmax = 16;                               // widest window the strip form of the gradient handles
 
 __device__ __forceinline__ double rsqrt_fast_d(double x) {
     double y;
@@ -818,11 +821,18 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) replay
         if (row == 0) {
 #pragma unroll
             for (int i = 0; i < D; ++i) vec[DP + i] = v[i];
+            ired[8] = 1 << 20; ired[9] = -1;             // window of the eigen-indices that carry weight (below)
+            ired[10] = 1 << 20; ired[11] = -1;           // ... and the wider one the gradient uses
         }
         __syncthreads();
         double ei = 0.0, ci = 0.0, wre = 1.0, wim = 0.0, zr = 0.0, zi = 0.0;
         if (row < D) {
             ci = (row < d) ? vec[DP + row] : 0.0;
+            // c_i = V[0][i] decays fast away from the initial state's energy: eigen-indices with |c_i| <= 1e-14 cannot move <n(t)>
+            // by more than 2 N d 1e-14, so the evolution only runs over the window [lo, hi] that holds the others (dimer
+            // N=100: 10 of 101 columns on average, trimer N=10: 55 of 66)
+            if (fabs(ci) > kCsigBig) { atomicMin(&ired[8], row); atomicMax(&ired[9], row); }
+            if (fabs(ci) > kCsigGrad) { atomicMin(&ired[10], row); atomicMax(&ired[11], row); }
             ei = (row < d) ? a.bs.ev[(size_t)b * d + row] : 0.0;
             const double th = ei * dt;
             const double lo = fma(ei, dt, -th);          // exact product tail
@@ -872,6 +882,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) replay
                     }
                 }
                 __syncthreads();
+                const int ks_lo = ired[8] & ~3, ks_hi = (ired[9] < 0) ? 0 : (((ired[9] & ~3) + 4 < KP) ? (ired[9] & ~3) + 4 : KP);
                 double2 acc[MTW][kNC / 8];
 #pragma unroll
                 for (int m = 0; m < MTW; ++m)
@@ -882,7 +893,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) replay
                     constexpr int NMT = decltype(Cc)::value + 1;
                     if (nmt == NMT) {
 #pragma unroll 4
-                        for (int ks = 0; ks < KP; ks += 4) {
+                        for (int ks = ks_lo; ks < ks_hi; ks += 4) {
                             double bf[kNC / 8], af[NMT];
 #pragma unroll
                             for (int n = 0; n < kNC / 8; ++n) bf[n] = lds64(baddr + (unsigned)((8 * n * LDZ + ks) * 8));
@@ -1035,6 +1046,48 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) replay
         }
         __syncthreads();                                 // V in shared memory is dead: the kernel S takes its place
         BPHASE_MARK(7);
+        // Every term of the gradient kernel carries c_i or c_j (K_ij = c_j (...)), and c decays fast away from the initial state's
+        // energy: with W = [wlo, whi] the window of |c_i| > 1e-18, only the pairs with a member in W count -- a D x |W| STRIP
+        //   T[i][j] = K_jj (i = j),  S_ij / 2 (i in W),  S_ij (i outside W)          G_row = 2 sum_{j in W} V_j sum_i T[i][j] V_i
+        // instead of the D^2 / 2 pairs (dimer N=100: |W| = 10 on average: a fifth of the divisions and of the row-sum work).
+        // V stays in shared memory (the strip lives in the dead phase-table region), V_j comes from there.
+        const int wlo = ired[10], nW = ired[11] - ired[10] + 1;
+        const bool use_strip = L::CYC && nW >= 1 && nW <= kWmax;
+        if constexpr (L::CYC) {
+            if (use_strip) {
+                double* strip = ph + L::ZM;                  // [kWmax][DP]
+                if (row < D) {
+                    const double br_i = fma(ar_, fr, -(ai_ * fi)), bim_i = vec[7 * DP + row];
+                    const bool in_w = (row >= wlo) && (row < wlo + nW);
+#pragma unroll 2
+                    for (int jw = 0; jw < nW; ++jw) {
+                        const int j = wlo + jw;
+                        const double dl = ei - vec[j];
+                        const double c_j = vec[DP + j], fjr = vec[2 * DP + j], fji = vec[3 * DP + j];
+                        const double kij = c_j * (br_i - ar_ * fjr + ai_ * fji);
+                        const double kji = ci * (vec[6 * DP + j] - vec[4 * DP + j] * fr + vec[5 * DP + j] * fi);
+                        double val;
+                        if (j == row) val = ci * ts * bim_i;                       // K_ii = c_i t* Im(b_i)
+                        else {
+                            if (fabs(dl * ts) < 1e-2) {
+                                // near-degenerate: Phi_ij = ts f_j (exp(-i x) - 1)/x ; S = Re[(a_i c_j + a_j c_i) Phi_ij]
+                                double gr, gi;
+                                expm1_over_x(dl * ts, gr, gi);
+                                const double phr = ts * (fjr * gr - fji * gi), phi = ts * (fjr * gi + fji * gr);
+                                const double mr = ar_ * c_j + vec[4 * DP + j] * ci;
+                                const double mi = ai_ * c_j + vec[5 * DP + j] * ci;
+                                val = mr * phr - mi * phi;
+                            } else {
+                                val = (kij - kji) * fast_rcp(dl);
+                            }
+                            if (in_w) val *= 0.5;                                 // pairs inside the window appear twice
+                        }
+                        strip[(size_t)jw * DP + row] = (row < d) ? val : 0.0;
+                    }
+                }
+            }
+        }
+        if (!use_strip) {
         if (row < D) sp[row] = (row < d) ? ci * ts * vec[7 * DP + row] : 0.0;      // K_ii = c_i t* Im(b_i)
         // S_ij = K_ij + K_ji.  Thread i pairs its own eigen-index (e, c, f, a, b in registers) with j = (i + o) mod D,
         // o = 1 .. D/2: every index pair once, the partner's values come from consecutive addresses across the warp
@@ -1126,11 +1179,29 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) replay
             }
         }
         }
+        }
         __syncthreads();
         BPHASE_MARK(8);
         // G_row = 2 [sum_i K_ii V_i^2 + sum_{i<j} S_ij V_i V_j], every index static
         double Gm = 0.0;
-        {
+        if (use_strip) {
+            if constexpr (L::CYC) {
+                const unsigned ts_a = smem_addr(ph + L::ZM);
+                const double* vrow = vsm + (size_t)(row < d ? row : 0) * LDV + wlo;
+#pragma unroll 1
+                for (int jw = 0; jw < nW; ++jw) {
+                    const unsigned ta = ts_a + (unsigned)(jw * DP * 8);
+                    double acc0 = 0.0, acc1 = 0.0;
+                    static_for<(D + 1) / 2>([&](auto Ic) {
+                        constexpr int i = 2 * decltype(Ic)::value;
+                        const double2 t2 = lds128(ta + i * 8);
+                        acc0 = fma(t2.x, v[i], acc0);
+                        if constexpr (i + 1 < D) acc1 = fma(t2.y, v[i + 1], acc1);
+                    });
+                    Gm = fma(vrow[jw], acc0 + acc1, Gm);
+                }
+            }
+        } else {
             const double2* sp2 = reinterpret_cast<const double2*>(sp + DP);
             double2 cur = make_double2(0.0, 0.0);
             if constexpr (L::CYC) {
