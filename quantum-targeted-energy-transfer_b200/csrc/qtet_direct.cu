@@ -699,7 +699,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) direct_kernel(SplitArgs a) {
             }
         }
         PHASE_MARK(1);
-        evolve_and_grad<D, G, true>(a, v, wsite, lv, part, sbuf, zbuf, cbuf, p, valid, g, q, lane, dt, _t0, evs, ncol, nsig, vt, LDV);
+        evolve_and_grad<D, G, true>(a, v, wsite, lv, part, sbuf, zbuf, cbuf, p, valid, g, q, lane, dt, _t0, evs, ncol, nsig);
     }
 }
 

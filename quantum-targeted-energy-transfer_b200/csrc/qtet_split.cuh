@@ -137,165 +137,6 @@ struct BLayout {
     static constexpr int PER_WARP = ((PHASED + ZB + PPW * D) + 1) & ~1;    // + c vector [PPW][D]
 };
 
-#ifndef QTET_EVO_PAIRS
-#define QTET_EVO_PAIRS 0   // 1: pair-cosine time evolution in the direct kernel when at most kPairCols columns carry weight.
-                           // Measured: parity-green and 16 % SLOWER on the config-2 grid (8.41 vs 7.25 ms) -- half the FP64
-                           // instructions of the column form, but the pair bookkeeping (per-slot selects, index arithmetic, one
-                           // LDS per FMA while M is built, a quarter of the lanes idle at 12 columns) costs what it saves.
-#endif
-constexpr int kPairCols = 16;              // widest significant window the pair form handles (wider ones take the column form)
-constexpr int kPairChunk = 16;             // time samples reduced across the lanes of a point at a time
-
-// ------------------------------------------------------------------------------------------------
-// Pair-cosine time evolution (direct path, G = 8 lanes per point).
-//   <n(t)> = sum_m n_m |sum_i V_mi c_i exp(-i e_i t)|^2 = sum_{i,j} c_i c_j M_ij cos((e_i - e_j) t),   M = V^T diag(n_site) V
-// Only the n_c columns with |c_i| > kCsig carry weight (11.7 of 21 on the config-2 grid): M restricted to them costs
-// n_c^2 / 2 * d FMAs ONCE, and a time sample then costs one FMA per index pair -- y_{k+1} = 2 cos(theta) y_k - y_{k-1} with
-// y_k = W_ij cos(k theta_ij), theta_ij = (e_i - e_j) dt, the Chebyshev recurrence (rounding grows like k^2 eps / 2 = 5e-14 of
-// the term at k = 30) -- instead of 2 d n_c FMAs for psi(t): 3x fewer FP64 instructions over the whole trace.
-// cos(theta_ij) comes from the per-eigenvalue unit steps, Re(w_i conj(w_j)): no extra sincos.
-// Layout: V goes to shared memory (its registers hold the pair state meanwhile and are reloaded at the end); lane q of a point
-// owns the rows i1 = q and i2 = n_c - 1 - q of the lower-triangular pair matrix (q + 1 and n_c - q pairs: n_c + 1 per lane
-// whatever q), so V[m][i1], V[m][i2] are loaded once per row m and every further load is the partner V[m][j].
-// Per-lane partial sums of a chunk of samples cross the lanes through shared memory (lane q finishes samples q, q + 8, ...).
-// ------------------------------------------------------------------------------------------------
-template <int D, int G>
-__device__ __forceinline__ void evolve_pairs(const SplitArgs& a, double (&v)[BLayout<D, G>::R][D],
-                                             const double (&wsite)[BLayout<D, G>::R], double* vst, int ldv, double* zb,
-                                             const double (&ci)[BLayout<D, G>::RZ], const double (&wre)[BLayout<D, G>::RZ],
-                                             const double (&wim)[BLayout<D, G>::RZ], long long p, bool valid, int g, int q,
-                                             int ncol, int nsig, double& vbest, int& kbest) {
-    using L = BLayout<D, G>;
-    constexpr int R = L::R, RZ = L::RZ, PPW = L::PPW, TMAX = kPairCols + 1;
-    static_assert(G == 8, "the lane map of the pair form assumes eight lanes per point");
-    const int T = a.pv.T;
-    // shared-memory carve-up of zb (ZB = 16 PPW D / ... doubles, at least 4 PPW D + D): [cz | wr | wi][PPW][D], wsm[D]; later the chunk buffer
-    double* cz = zb;
-    double* wr = zb + PPW * D;
-    double* wi = zb + 2 * PPW * D;
-    double* wsm = zb + 3 * PPW * D;
-    double* vg = vst + (size_t)g * D * ldv;
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
-        const int row = q * R + k;
-        if (row < D) {
-#pragma unroll
-            for (int i = 0; i < D; ++i) vg[row * ldv + i] = v[k][i];
-            if (g == 0) wsm[row] = wsite[k];
-        }
-    }
-#pragma unroll
-    for (int t = 0; t < RZ; ++t) {
-        const int i = q + t * G;
-        if (i < D) { cz[g * D + i] = ci[t]; wr[g * D + i] = wre[t]; wi[g * D + i] = wim[t]; }
-    }
-    __syncwarp();
-    // the lane map follows the point's OWN count (results must not depend on the warp's other points), the loop bounds the warp's
-    const int Ts = ((ncol + 1) & ~1) + 1;                            // warp-uniform
-    const int nc = (((nsig < 1 ? 1 : nsig) + 1) & ~1), half = nc >> 1;
-    const bool act = q < half;
-    const int i1 = act ? q : 0, i2 = act ? nc - 1 - q : 0;
-    double ya[TMAX], yb[TMAX], x2[TMAX];
-#pragma unroll
-    for (int t = 0; t < TMAX; ++t) ya[t] = 0.0;
-    // ---- M_ij of my pairs
-#pragma unroll 3
-    for (int m = 0; m < D; ++m) {
-        const double nm = wsm[m];
-        const double* vr = vg + m * ldv;
-        const double a1 = nm * vr[i1], a2 = nm * vr[i2];
-#pragma unroll
-        for (int t0 = 0; t0 < TMAX; t0 += 3) {
-            if (t0 >= Ts) break;
-#pragma unroll
-            for (int u = 0; u < 3; ++u) {
-                const int t = t0 + u;
-                if (t < TMAX) {
-                    const bool first = t <= q;
-                    int j = first ? t : t - q - 1;
-                    j = (j < D) ? j : 0;
-                    ya[t] = fma(first ? a1 : a2, vr[j], ya[t]);
-                }
-            }
-        }
-    }
-    // ---- weights and the recurrence start:  ya = W cos(0) = W,  yb = W cos(theta),  x2 = 2 cos(theta)
-    {
-        const double c1 = cz[g * D + i1], c2 = cz[g * D + i2];
-        const double r1 = wr[g * D + i1], r2 = wr[g * D + i2], m1 = wi[g * D + i1], m2 = wi[g * D + i2];
-#pragma unroll
-        for (int t = 0; t < TMAX; ++t) {
-            const bool first = t <= q;
-            int j = first ? t : t - q - 1;
-            const int i = first ? i1 : i2;
-            const bool live = act && (t <= nc) && (j <= i) && (j < D);
-            j = (j < D) ? j : 0;
-            const double cs = fma(first ? r1 : r2, wr[g * D + j], (first ? m1 : m2) * wi[g * D + j]);
-            double w = (first ? c1 : c2) * cz[g * D + j] * ya[t];
-            w = (i == j) ? w : 2.0 * w;
-            w = live ? w : 0.0;
-            ya[t] = w; yb[t] = w * cs; x2[t] = 2.0 * cs;
-        }
-    }
-    __syncwarp();                                        // cz / wr / wi are dead: the chunk buffer takes their place
-    double* ch = zb + (size_t)g * G * kPairChunk;        // [G lanes][kPairChunk]
-    kbest = -1; vbest = 0.0;
-    for (int k0 = 0; k0 < T; k0 += kPairChunk) {
-        const int kend = (T - k0 < kPairChunk) ? (T - k0) : kPairChunk;
-#pragma unroll 1
-        for (int kk = 0; kk < kend; kk += 2) {
-            double s0a = 0.0, s0b = 0.0, s1a = 0.0, s1b = 0.0;
-#pragma unroll
-            for (int t0 = 0; t0 < TMAX; t0 += 3) {
-                if (t0 >= Ts) break;
-#pragma unroll
-                for (int u = 0; u < 3; ++u) {
-                    const int t = t0 + u;
-                    if (t < TMAX) {
-                        if (u & 1) { s0b += ya[t]; s1b += yb[t]; } else { s0a += ya[t]; s1a += yb[t]; }
-                        ya[t] = fma(x2[t], yb[t], -ya[t]);           // y_{k+2}
-                        yb[t] = fma(x2[t], ya[t], -yb[t]);           // y_{k+3}
-                    }
-                }
-            }
-            ch[q * kPairChunk + kk] = s0a + s0b;
-            if (kk + 1 < kPairChunk) ch[q * kPairChunk + kk + 1] = s1a + s1b;
-        }
-        __syncwarp();
-        // lane q finishes the samples q, q + 8 of the chunk: fixed summation order over the lanes
-#pragma unroll
-        for (int h = 0; h < kPairChunk / G; ++h) {
-            const int kk = q + h * G;
-            if (kk < kend) {
-                double sum = 0.0;
-#pragma unroll
-                for (int qq = 0; qq < G; ++qq) sum += ch[qq * kPairChunk + kk];
-                const int k = k0 + kk;
-                if (a.trace && valid) a.trace[p * T + k] = sum;
-                const double key = a.acceptor ? sum : -sum;
-                if (kbest < 0 || key > vbest) { vbest = key; kbest = k; }
-            }
-        }
-        __syncwarp();
-    }
-    // the lanes hold disjoint samples: first extremum over all of them (ties: the earlier sample)
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, vbest, o);
-        const int ok = __shfl_xor_sync(0xffffffffu, kbest, o);
-        if (ok >= 0 && (kbest < 0 || ov > vbest || (ov == vbest && ok < kbest))) { vbest = ov; kbest = ok; }
-    }
-    // ---- my rows of V back into their registers
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
-        const int row = q * R + k;
-#pragma unroll
-        for (int i = 0; i < D; ++i) v[k][i] = (row < D) ? vg[row * ldv + i] : 0.0;
-    }
-    __syncwarp();
-}
-
 // ------------------------------------------------------------------------------------------------
 // Phases after the eigendecomposition, shared by apply_kernel (rotation replay) and direct_kernel
 // (two-sided recurrences).  G lanes per point, lane q holds rows q*R .. q*R+R-1 of V in v[][].
@@ -313,8 +154,7 @@ __device__ __forceinline__ void evolve_and_grad(const SplitArgs& a, double (&v)[
                                                 const double (&wsite)[BLayout<D, G>::R], double* lv, double2* part,
                                                 double* sbuf, double2* zbuf, double* cbuf, long long p, bool valid,
                                                 int g, int q, int lane, double dt, long long& _t0,
-                                                const double* evs = nullptr, int ncol = D, int nsig = D,
-                                                double* vstore = nullptr, int ldvs = 0) {
+                                                const double* evs = nullptr, int ncol = D, int nsig = D) {
     using L = BLayout<D, G>;
     constexpr int R = L::R, RZ = L::RZ, PPW = L::PPW, NP = L::NP;
     const ProblemView& pv = a.pv;
@@ -349,17 +189,8 @@ __device__ __forceinline__ void evolve_and_grad(const SplitArgs& a, double (&v)[
     // ---- time evolution: n(t_k) = sum_rows n_site |psi_row(t_k)|^2, running arg-max / arg-min
     int kbest = -1;
     double vbest = 0.0;
-    bool pairs_done = false;
-#if QTET_EVO_PAIRS
-    if constexpr (PERM && G == 8 && D >= 16) {
-        if (vstore != nullptr && ncol <= kPairCols) {          // warp-uniform
-            evolve_pairs<D, G>(a, v, wsite, vstore, ldvs, reinterpret_cast<double*>(zbuf), ci, wre, wim, p, valid, g, q, ncol, nsig, vbest, kbest);
-            pairs_done = true;
-        }
-    }
-#endif
     // two samples per pass: every V element is read once for four fmas (operand reuse), the pass overhead halves
-    for (int k = 0; k < T && !pairs_done; k += 2) {
+    for (int k = 0; k < T; k += 2) {
         double2* zb0 = zbuf + ((((k >> 1) & 1) * 2 + 0) * PPW + g) * D;
         double2* zb1 = zbuf + ((((k >> 1) & 1) * 2 + 1) * PPW + g) * D;
 #pragma unroll
