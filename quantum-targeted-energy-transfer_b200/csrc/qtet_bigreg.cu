@@ -454,9 +454,13 @@ __device__ __forceinline__ int rec_key(double sp, double sq, int e) {      // ~ 
 
 // Column `i` of Z (eigenvector of the tridiagonal (sa, sb) for eigenvalue lam), normalised, into zc[k * ld], k < d.
 // Returns false when the recurrences produced something unusable (NaN / overflow): the point then takes the fallback.
+// Scale epochs: a rescale of the bottom-up pass at entry k applies to the entries <= k; the (few) positions are kept as a stack of
+// 7-bit fields in one 64-bit word, smallest position in the low bits, so that the top-down passes meet them in order with one
+// compare per step; the factors that bring an entry to the scale of the join row change only at those events.
 __device__ __forceinline__ bool direct_column(int d, double lam, const double* __restrict__ sa, const double* __restrict__ sb,
                                               const double* __restrict__ sib, double* zc, int ld) {
-    unsigned long long qlo = 0ull, qhi = 0ull;           // bit k: the bottom-up pass rescaled at entry k (applies to entries <= k)
+    unsigned long long qev = ~0ull;                      // event stack (127 = none)
+    int eq0 = 0;                                         // scale epoch of q_0 = number of events
     // from the bottom: q_{k-1} = ((lam - a_k) q_k - b_k q_{k+1}) / b_{k-1},  q_{d-1} = 1
     {
         double qn = 0.0, qc = 1.0;
@@ -467,23 +471,26 @@ __device__ __forceinline__ bool direct_column(int d, double lam, const double* _
             qn = qc; qc = val;
             if (fabs(qc) > kRecBig) {
                 qc *= kRecF; qn *= kRecF;
-                if (k - 1 < 64) qlo |= 1ull << (k - 1); else qhi |= 1ull << (k - 1 - 64);
+                qev = (qev << 7) | (unsigned long long)(k - 1);
+                ++eq0;
             }
             zc[(size_t)(k - 1) * ld] = qc;
         }
     }
-    const int eq0 = __popcll(qlo) + __popcll(qhi);       // scale epoch of q_0
-    auto qbit = [&](int k) -> int { return (int)(((k < 64) ? (qlo >> k) : (qhi >> (k - 64))) & 1ull); };
+    if (eq0 > 8) return false;                           // (cannot happen below 2^2048 of growth; the stack holds nine fields)
+    constexpr unsigned long long kRefill = 127ull << 57;
     // from the top: p_{k+1} = ((lam - a_k) p_k - b_{k-1} p_{k-1}) / b_k,  p_0 = 1; join row r = argmax |p_k q_k|
     int r = 0, epr = 0, eqr = eq0;
     double pr = 1.0, qr = zc[0];
     {
         double pm = 0.0, pc = 1.0;
         int ep = 0, eq = eq0;
+        unsigned long long qs = qev;
+        int nextq = (int)(qs & 127ull);
         int best = rec_key(1.0, qr, eq0);
 #pragma unroll 4
         for (int k = 0; k < d - 1; ++k) {
-            eq -= qbit(k);                                // epoch of q_{k+1}
+            if (k == nextq) { --eq; qs = (qs >> 7) | kRefill; nextq = (int)(qs & 127ull); }      // epoch of q_{k+1}
             const double bm = (k >= 1) ? sb[k - 1] : 0.0;
             const double pn = fma(lam - sa[k], pc, -(bm * pm)) * sib[k];
             pm = pc; pc = pn;
@@ -493,26 +500,34 @@ __device__ __forceinline__ bool direct_column(int d, double lam, const double* _
             if (ky > best) { best = ky; r = k + 1; pr = pc; qr = sq; epr = ep; eqr = eq; }
         }
     }
-    // second pass from the top: z_k = p_k / p_r above the join, q_k / q_r from the join down
-    const double invp = fast_rcp(pr), invq = fast_rcp(qr);
+    // z_k = p_k / p_r above the join (the recurrence once more, up to the join only), q_k / q_r from the join down
     double ss = 0.0;
     {
-        double pm = 0.0, pc = 1.0;
-        int ep = 0, eq = eq0;
+        const double invp = fast_rcp(pr);
+        double pm = 0.0, pc = 1.0, fp = rec_scale(epr) * invp;
+        int ep = 0;
 #pragma unroll 4
-        for (int k = 0; k < d; ++k) {
-            const bool above = k < r;
-            const double raw = above ? pc : zc[(size_t)k * ld];
-            const double x = raw * rec_scale(above ? (epr - ep) : (eqr - eq)) * (above ? invp : invq);
+        for (int k = 0; k < r; ++k) {
+            const double x = pc * fp;
             zc[(size_t)k * ld] = x;
             ss = fma(x, x, ss);
-            if (k < d - 1) {
-                eq -= qbit(k);
-                const double bm = (k >= 1) ? sb[k - 1] : 0.0;
-                const double pn = fma(lam - sa[k], pc, -(bm * pm)) * sib[k];
-                pm = pc; pc = pn;
-                if (fabs(pc) > kRecBig) { pc *= kRecF; pm *= kRecF; ++ep; }
-            }
+            const double bm = (k >= 1) ? sb[k - 1] : 0.0;
+            const double pn = fma(lam - sa[k], pc, -(bm * pm)) * sib[k];
+            pm = pc; pc = pn;
+            if (fabs(pc) > kRecBig) { pc *= kRecF; pm *= kRecF; ++ep; fp = rec_scale(epr - ep) * invp; }
+        }
+        const double invq = fast_rcp(qr);
+        unsigned long long qs = qev;
+        int nextq = (int)(qs & 127ull);
+        while (nextq < r) { qs = (qs >> 7) | kRefill; nextq = (int)(qs & 127ull); }    // events above the join row are behind us
+        int eq = eqr;
+        double fq = invq;
+#pragma unroll 4
+        for (int k = r; k < d; ++k) {
+            const double x = zc[(size_t)k * ld] * fq;
+            zc[(size_t)k * ld] = x;
+            ss = fma(x, x, ss);
+            if (k == nextq) { --eq; qs = (qs >> 7) | kRefill; nextq = (int)(qs & 127ull); fq = rec_scale(eqr - eq) * invq; }
         }
     }
     const bool ok = (ss >= 0.5 && ss < 1e300);           // z_r = 1: |z|^2 >= 1 unless NaN / overflow
