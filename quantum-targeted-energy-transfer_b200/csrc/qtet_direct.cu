@@ -882,8 +882,14 @@ int launch_direct(const ProblemView& pv, DirectWorkspace** wsp, const double* ch
     for (int k = 0; k < 32; ++k) { a.boff[k] = ws->boff[k]; a.iboff[k] = ws->iboff[k]; }
     a.n_dev = n_dev;                      // a device-side count only makes sense for a single chunk (the optimiser's case)
 
-    QTET_CUDA(cudaEventRecord(ws->ev_fork, st));
-    QTET_CUDA(cudaStreamWaitEvent(ws->aux, ws->ev_fork, 0));
+    // One chunk with a device-side count (the optimiser's epoch): K_E and K_D run back to back on the caller's stream -- nothing
+    // could overlap, and the two cross-stream hops would only add their scheduling latency to every epoch.
+    const bool inline_e = (n_dev != nullptr);
+    cudaStream_t se = inline_e ? st : ws->aux;
+    if (!inline_e) {
+        QTET_CUDA(cudaEventRecord(ws->ev_fork, st));
+        QTET_CUDA(cudaStreamWaitEvent(ws->aux, ws->ev_fork, 0));
+    }
     int c = 0;
     for (long long lo = 0; lo < B; lo += chunk, ++c) {
         const int buf = c & 1;
@@ -896,19 +902,21 @@ int launch_direct(const ProblemView& pv, DirectWorkspace** wsp, const double* ch
         a.tstar = tstar ? tstar + lo : nullptr;
         a.trace = trace ? trace + lo * pv.T : nullptr;
         // K_E(c) on aux, after K_D(c-2) and its fallback released this buffer
-        if (c >= 2) QTET_CUDA(cudaStreamWaitEvent(ws->aux, ws->ev_d[buf], 0));
-        if (hook && hook->before) { const int hrc = hook->before(hook->ctx, lo, n, ws->aux); if (hrc) return hrc; }
+        if (c >= 2 && !inline_e) QTET_CUDA(cudaStreamWaitEvent(ws->aux, ws->ev_d[buf], 0));
+        if (hook && hook->before) { const int hrc = hook->before(hook->ctx, lo, n, se); if (hrc) return hrc; }
         long long gridE = (long long)ws->sms * ws->per_sm_e;
         const long long needE = ((n + 31) / 32 + kWarpsE - 1) / kWarpsE;
         if (gridE > needE) gridE = needE;
-        if (prof) prof->begin(0, n, ws->aux);
-        eig_scalar_kernel<<<(unsigned)gridE, kWarpsE * 32, ws->smem_e, ws->aux>>>(a);
+        if (prof) prof->begin(0, n, se);
+        eig_scalar_kernel<<<(unsigned)gridE, kWarpsE * 32, ws->smem_e, se>>>(a);
         count_launch();
-        if (prof) prof->finish(0, ws->aux);
+        if (prof) prof->finish(0, se);
         QTET_CUDA(cudaGetLastError());
-        QTET_CUDA(cudaEventRecord(ws->ev_e[buf], ws->aux));
-        // K_D(c) on the caller's stream
-        QTET_CUDA(cudaStreamWaitEvent(st, ws->ev_e[buf], 0));
+        if (!inline_e) {
+            QTET_CUDA(cudaEventRecord(ws->ev_e[buf], ws->aux));
+            // K_D(c) on the caller's stream
+            QTET_CUDA(cudaStreamWaitEvent(st, ws->ev_e[buf], 0));
+        }
         if (prof) prof->begin(1, n, st);
         switch (ws->D) {
             case 4: rc = launch_direct_kernel<4, 4, 4, 4, false>(a, ws->cfg_d, ws->sms, st); break;
@@ -924,7 +932,7 @@ int launch_direct(const ProblemView& pv, DirectWorkspace** wsp, const double* ch
         // numerically degenerate points (if any) are recomputed by the fused generic kernel
         rc = launch_generic_list(pv, a.chis, a.fb_list, a.fb_count, n, site, a.loss, a.grad, a.tstar, a.trace, st);
         if (rc) return rc;
-        QTET_CUDA(cudaEventRecord(ws->ev_d[buf], st));
+        if (!inline_e) QTET_CUDA(cudaEventRecord(ws->ev_d[buf], st));
         if (hook && hook->after) { const int hrc = hook->after(hook->ctx, lo, n, st); if (hrc) return hrc; }
     }
     return QTET_OK;
