@@ -18,7 +18,10 @@
  *   - return value 0 = success, negative = failure (QTET_E*); qtet_last_error() returns a
  *     thread-local human-readable message.  No exception crosses the ABI.
  *   - one process per GPU; a handle is bound to the device it was created on and may be used
- *     from one thread at a time.
+ *     from one thread and on one stream at a time (its workspaces are ordered against the stream
+ *     of the call that uses them); entry points switch to the handle's device and restore the caller's;
+ *   - Fock dimensions up to 1536 (d <= 115: register / shared-memory kernels; above: the generic kernel with its
+ *     matrices in global memory); larger systems are refused by qtet_problem_create.
  */
 #ifndef QTET_H_
 #define QTET_H_

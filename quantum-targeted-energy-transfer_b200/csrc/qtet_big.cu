@@ -605,7 +605,7 @@ int launch_big(const ProblemView& pv, BigWorkspace** wsp, const double* chis, in
                              32 * ((size_t)d * 8 + 4 + (dense ? (2 * (size_t)d * 8 + (size_t)d * d * 8) : 0));
     // The scalar QL kernel is a serial chain per point (milliseconds per batch of 32 points, whatever the machine
     // load): its cost is amortised only if MANY batches are in flight, so the chunk takes what the card can spare --
-    // up to 40 % of the free HBM, at most 48 GiB (B200: 180 GB) -- rather than a fixed few GiB.
+    // up to 40 % of the free HBM, at most 8 GiB (QTET_BIG_WS_GIB overrides) -- rather than a fixed few hundred MiB.
     const long long all_b0 = (B + 31) / 32;
     if (ws->budget == 0 || (size_t)all_b0 * per_batch > ws->blob_bytes) {      // (re)query only when the buffer would have to grow
         size_t budget = (size_t)4 << 30;
@@ -613,7 +613,7 @@ int launch_big(const ProblemView& pv, BigWorkspace** wsp, const double* chis, in
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
             const size_t avail = free_b + ws->blob_bytes;           // our own blob is reusable
             size_t want = (size_t)(0.4 * (double)avail);
-            if (want > ((size_t)48 << 30)) want = (size_t)48 << 30;
+            if (want > ((size_t)8 << 30)) want = (size_t)8 << 30;      // 8 GiB holds > 45 000 points per launch at d = 101: every warp slot busy
             if (want > budget) budget = want;
         } else cudaGetLastError();
         if (const char* env = std::getenv("QTET_BIG_WS_GIB")) { const double g = std::atof(env); if (g > 0) budget = (size_t)(g * 1073741824.0); }

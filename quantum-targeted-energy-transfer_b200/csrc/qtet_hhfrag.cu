@@ -581,9 +581,15 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) hh_fra
         if constexpr (MODE == 3) {
             // reflectors of stage A back into shared memory, X_B (stage B) into the trailing block of X
             const double* rf = a_.rfl + (size_t)b * koff * (DP + 1);
-            for (int i = tid; i < koff * (DP + 1); i += NT) {
-                const int k = i / (DP + 1), c = i - k * (DP + 1);
-                if (c < DP) refl[(size_t)(k + 1) * DP + c] = rf[i]; else s_beta[k] = rf[i];
+            constexpr int KOFF = 8 * KBS;                        // = koff: all loads of a thread are independent and issue together
+            for (int c = tid; c < DP + 1; c += NT) {
+                double tmp[KOFF > 0 ? KOFF : 1];
+#pragma unroll
+                for (int k = 0; k < KOFF; ++k) tmp[k] = __ldg(rf + k * (DP + 1) + c);
+#pragma unroll
+                for (int k = 0; k < KOFF; ++k) {
+                    if (c < DP) refl[(size_t)(k + 1) * DP + c] = tmp[k]; else s_beta[k] = tmp[k];
+                }
             }
             const double* q = a_.qmat + (size_t)b * d * d;
 #pragma unroll
