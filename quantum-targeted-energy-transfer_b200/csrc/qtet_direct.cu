@@ -56,6 +56,11 @@ __device__ __forceinline__ double diag_entry(const double* lin, const double* qu
 #ifndef QTET_PREFETCH_NEXT
 #define QTET_PREFETCH_NEXT 0  // 1: prefetch the next task's chi / eigenvalues into L1 at the top of a task
 #endif
+#ifndef QTET_REC_FUSED
+#define QTET_REC_FUSED 0   // 1: bottom-up and top-down recurrences of K_D in one unrolled loop, p_k in registers (see there).
+                           // Bit-identical results, 27 % fewer executed instructions -- and measured SLOWER (8.04 vs 7.27 ms per
+                           // grid): like every unrolled variant of this kernel it loses on instruction fetch what it saves.
+#endif
 #ifndef QTET_REC_ROLLED
 #define QTET_REC_ROLLED 1  // 1: the three recurrence passes of K_D as rolled loops (small code), 0: fully unrolled with register-resident constants
 #endif
@@ -406,7 +411,84 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) direct_kernel(SplitArgs a) {
         double* colp[RZ];
 #pragma unroll
         for (int t = 0; t < RZ; ++t) { const int i = q + t * G; colp[t] = vp + ((i < D) ? i : (D - 1)); }   // i >= D: nothing is stored
-#if QTET_REC_ROLLED
+#if QTET_REC_FUSED
+        // FUSED: the bottom-up (q) and the top-down (p) recurrence are independent, so they run in ONE unrolled loop -- six
+        // dependency chains per lane instead of three -- with every p_k kept in a register (V's registers are still free here);
+        // the join search and the final scaling are then plain loops over k without a recurrence (and without the third pass
+        // that recomputed p).  Same operations in the same order per eigen-index as the rolled passes: bit-identical results.
+        double invp[RZ], invq[RZ];
+        int rj[RZ];
+        {
+            double preg[RZ][D];
+            double qn[RZ], qc[RZ], pm[RZ], pc[RZ];
+#pragma unroll
+            for (int t = 0; t < RZ; ++t) {
+                qn[t] = 0.0; qc[t] = (D - 1 == d - 1) ? 1.0 : 0.0;
+                if (q + t * G < D) colp[t][(D - 1) * LDV] = qc[t];
+                pm[t] = 0.0; pc[t] = 1.0; preg[t][0] = 1.0;
+            }
+#pragma unroll
+            for (int s = 0; s < D - 1; ++s) {
+                const int k = D - 1 - s;                       // q_{k-1} from the bottom, p_{s+1} from the top
+                const double ak = ap[k], bk = sb[k], ibm = sib[k - 1];
+                const double ak2 = ap[s], bm2 = (s >= 1) ? sb[s - 1] : 0.0, ib2 = sib[s];
+#pragma unroll
+                for (int t = 0; t < RZ; ++t) {
+                    double val = fma(lam[t] - ak, qc[t], -(bk * qn[t])) * ibm;
+                    if (!EXACT && k - 1 == d - 1) val = 1.0;
+                    qn[t] = qc[t]; qc[t] = val;
+                    if (q + t * G < D) colp[t][(k - 1) * LDV] = val;
+                    const double pn = fma(lam[t] - ak2, pc[t], -(bm2 * pm[t])) * ib2;
+                    pm[t] = pc[t]; pc[t] = pn;
+                    preg[t][s + 1] = pn;
+                }
+            }
+            __syncwarp();
+            PHASE_MARK(11);
+            // join row r = argmax |p_k q_k|
+            double best[RZ], pr[RZ], qr[RZ];
+#pragma unroll
+            for (int t = 0; t < RZ; ++t) {
+                const double q0 = colp[t][0];
+                best[t] = fabs(q0); rj[t] = 0; pr[t] = 1.0; qr[t] = q0;
+            }
+#pragma unroll
+            for (int k = 1; k < D; ++k) {
+#pragma unroll
+                for (int t = 0; t < RZ; ++t) {
+                    const double qk = colp[t][k * LDV];
+                    const double prod = fabs(preg[t][k] * qk);
+                    if (prod > best[t]) { best[t] = prod; rj[t] = k; pr[t] = preg[t][k]; qr[t] = qk; }
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < RZ; ++t) { invp[t] = fast_rcp(pr[t]); invq[t] = fast_rcp(qr[t]); }
+            PHASE_MARK(12);
+            // z_k = p_k / p_r above the join, q_k / q_r from the join down; 1 / |z| goes to rnbuf
+            double ss[RZ];
+#pragma unroll
+            for (int t = 0; t < RZ; ++t) ss[t] = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+#pragma unroll
+                for (int t = 0; t < RZ; ++t) {
+                    const int i = q + t * G;
+                    const bool above = k < rj[t];
+                    const double qk = colp[t][k * LDV];
+                    double x = (above ? preg[t][k] : qk) * (above ? invp[t] : invq[t]);
+                    if (!EXACT && i >= d) x = (k == i) ? 1.0 : 0.0;             // padded eigen-index: identity column
+                    if (i < D) colp[t][k * LDV] = x;
+                    ss[t] = fma(x, x, ss[t]);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < RZ; ++t) {
+                const int i = q + t * G;
+                if (i < d && !(ss[t] >= 0.5 && ss[t] < 1e300)) { fb = true; ss[t] = 1.0; }   // z_r = 1: |z|^2 >= 1 unless NaN / overflow
+                if (i < D) rnbuf[g * D + i] = (i < d) ? rsqrt_fast(ss[t]) : 1.0;
+            }
+        }
+#elif QTET_REC_ROLLED
         // ROLLED loops: the three passes are ~40 instructions each instead of ~1700 unrolled ones.  The kernel is a 7000-
         // instruction straight line per task and `no_instruction` was its third stall reason (profiles/r2_*): what need not be
         // unrolled (nothing here indexes a register array) is not.  Every operand of step k+1 is loaded during step k.
