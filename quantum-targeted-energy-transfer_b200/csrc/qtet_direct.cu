@@ -56,6 +56,10 @@ __device__ __forceinline__ double diag_entry(const double* lin, const double* qu
 #ifndef QTET_PREFETCH_NEXT
 #define QTET_PREFETCH_NEXT 0  // 1: prefetch the next task's chi / eigenvalues into L1 at the top of a task
 #endif
+#ifndef QTET_KD_MINB
+#define QTET_KD_MINB 4     // resident CTAs per SM the exact-size d = 21 instantiation of K_D is compiled for (register cap 65536 / (64 MINB)).
+                           // 5 (200 registers, 116 B of spills, 10 warps per SM) measured SLOWER: 8.25 vs 7.28 ms per grid.
+#endif
 #ifndef QTET_REC_FUSED
 #define QTET_REC_FUSED 0   // 1: bottom-up and top-down recurrences of K_D in one unrolled loop, p_k in registers (see there).
                            // Bit-identical results, 27 % fewer executed instructions -- and measured SLOWER (8.04 vs 7.27 ms per
@@ -300,8 +304,15 @@ struct DLayout {
 // K_D: G lanes per point; eigenvectors by two-sided recurrences, then the shared phases.
 // ------------------------------------------------------------------------------------------------
 // EXACT: the Fock dimension equals the template size (no padded rows / eigen-indices), d is a compile-time constant.
+// Register cap for MINB CTAs of WARPS warps per SM, given explicitly: `__launch_bounds__(threads, MINB)` rounds the CTA up when it
+// derives the cap (168 instead of 200 registers for five CTAs of two warps).
+constexpr int kd_reg_cap(int warps, int minb) {
+    int r = 65536 / (minb * warps * 32);
+    r = r / 8 * 8;
+    return r > 255 ? 255 : r;
+}
 template <int D, int G, int WARPS, int MINB, bool EXACT>
-__global__ void __launch_bounds__(WARPS * 32, MINB) direct_kernel(SplitArgs a) {
+__global__ void __launch_bounds__(WARPS * 32) __maxnreg__(kd_reg_cap(WARPS, MINB)) direct_kernel(SplitArgs a) {
     using L = BLayout<D, G>;
     using DL = DLayout<D, G>;
     constexpr int R = L::R, RZ = L::RZ, PPW = L::PPW, LDV = DL::LDV;
@@ -892,7 +903,7 @@ static int direct_workspace_init(const ProblemView& pv, DirectWorkspace** wsp) {
         case 4: rc = config_direct<4, 4, 4, 4, false>(ws->cfg_d); break;
         case 8: rc = config_direct<8, 8, 4, 4, false>(ws->cfg_d); break;
         case 16: rc = config_direct<16, 8, 2, 6, false>(ws->cfg_d); break;
-        case 21: rc = (pv.d == 21) ? config_direct<21, 8, 2, 4, true>(ws->cfg_d) : config_direct<21, 8, 2, 4, false>(ws->cfg_d); break;
+        case 21: rc = (pv.d == 21) ? config_direct<21, 8, 2, QTET_KD_MINB, true>(ws->cfg_d) : config_direct<21, 8, 2, 4, false>(ws->cfg_d); break;
         case 24: rc = config_direct<24, 8, 2, 4, false>(ws->cfg_d); break;
         default: rc = config_direct<32, 16, 2, 4, false>(ws->cfg_d); break;
     }
@@ -1004,7 +1015,7 @@ int launch_direct(const ProblemView& pv, DirectWorkspace** wsp, const double* ch
             case 4: rc = launch_direct_kernel<4, 4, 4, 4, false>(a, ws->cfg_d, ws->sms, st); break;
             case 8: rc = launch_direct_kernel<8, 8, 4, 4, false>(a, ws->cfg_d, ws->sms, st); break;
             case 16: rc = launch_direct_kernel<16, 8, 2, 6, false>(a, ws->cfg_d, ws->sms, st); break;
-            case 21: rc = (d == 21) ? launch_direct_kernel<21, 8, 2, 4, true>(a, ws->cfg_d, ws->sms, st)
+            case 21: rc = (d == 21) ? launch_direct_kernel<21, 8, 2, QTET_KD_MINB, true>(a, ws->cfg_d, ws->sms, st)
                                    : launch_direct_kernel<21, 8, 2, 4, false>(a, ws->cfg_d, ws->sms, st); break;
             case 24: rc = launch_direct_kernel<24, 8, 2, 4, false>(a, ws->cfg_d, ws->sms, st); break;
             default: rc = launch_direct_kernel<32, 16, 2, 4, false>(a, ws->cfg_d, ws->sms, st); break;

@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(NW * 32) __maxnreg__(reg_cap(NW, MINB)) hh_fra
                     const bool last = (k == d - 2);           // only the update of column d-3 is left
                     const unsigned par = (unsigned)(k & 1), pp = par ^ 1u;
                     const unsigned vprev_a = refl_a + (unsigned)(k * DP * 8), vcur_a = vprev_a + (unsigned)(DP * 8);
-                    const unsigned psp_a = ps_a + pp * (DP * 8), psc_a = ps_a + par * (DP * 8);
+                    const unsigned psp_a = ps_a + pp * (DP * 8);
                     const unsigned rowp_a = row_a + pp * (DP * 8), rowc_a = row_a + par * (DP * 8);
                     auto body = [&](auto J0c) {
                         constexpr int J0 = decltype(J0c)::value;
