@@ -153,6 +153,43 @@ np.savez(sys.argv[1], *[a for t in out for a in t])
             assert np.abs(a - b).max() < 1e-6 * max(1.0, np.abs(b).max())
 
 
+def test_householder_variants_agree():
+    """Dense large-d systems: the staged tiled Householder reduction (default), the same in one kernel (QTET_HH_STAGED=0), the
+    one-barrier-per-column variant (QTET_HH_FRAG=2) and round 1's one-row-per-thread kernel (QTET_HH_FRAG=0) are four
+    implementations of the same reduction -- losses, gradients and arg-max samples must agree to rounding."""
+    import subprocess
+    import sys
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = f"""
+import sys, numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'quantum-targeted-energy-transfer_b200')!r})
+from tet import _native
+out = []
+for N, om in [(10, [-3, 3, 3]), (6, [-3, 0, 1, 3]), (9, [-3, 3, 3])]:        # d = 66, 84 (both staged), 55 (staged, ragged tiles)
+    c = {{"max_N": N, "sites": len(om), "max_t": 25, "omegas": om, "chis": [0] * len(om), "coupling": 1, "timesteps": 30}}
+    X = np.random.default_rng(7).uniform(-10, 10, (200, len(om)))
+    p = _native.Problem.from_const(c)
+    L, g, k = p.loss_grad_host(X, len(om) - 1)
+    assert p.stats()["nonconverged"] == 0
+    out.append((L, g, k))
+np.savez(sys.argv[1], *[a for t in out for a in t])
+"""
+    res = []
+    for env in ({}, {"QTET_HH_STAGED": "0"}, {"QTET_HH_FRAG": "2"}, {"QTET_HH_FRAG": "0"}):
+        with tempfile.NamedTemporaryFile(suffix=".npz") as fh:
+            out = subprocess.run([sys.executable, "-c", code, fh.name], env={**os.environ, **env}, capture_output=True, text=True, timeout=900)
+            assert out.returncode == 0, (env, out.stderr[-2000:])
+            z = np.load(fh.name)
+            res.append([z[k] for k in z.files])
+    for other in res[1:]:
+        for a, b in zip(res[0], other):
+            if a.dtype.kind == "i":
+                assert (a == b).mean() > 0.99
+            else:
+                assert np.abs(a - b).max() < 1e-8 * max(1.0, np.abs(b).max())
+
+
 def test_large_d_chunked_workspace_matches_single_chunk():
     """The large-d path sizes its workspace from the free HBM; QTET_BIG_WS_GIB=0.25 forces several chunks per call.
     Chunked and unchunked evaluation must agree bit for bit (same kernels, same points)."""
