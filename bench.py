@@ -235,6 +235,7 @@ def measure_secondary(_native, torch, dev, local, flush, peak, name="trimer10", 
     w = WORKLOADS[name]
     const = make_const(w)
     prob = _native.Problem.from_const(const, device=local)
+    prob.set_locality_sort(w["kind"] == "random")
     path_name = _native.PATH_NAMES[prob.get_path()]
     pts = make_points(w)
     B, f = pts.shape
@@ -359,6 +360,7 @@ def run_config3_block(_native, torch, dev, local, rank, world, flush, peak, tota
     pts = np.random.default_rng(0).uniform(-10, 10, (total, 2))
     lo, hi = parallel.shard_bounds(total, rank, world)
     prob = _native.Problem.from_const(const, device=local)
+    prob.set_locality_sort(True)          # random points: evaluated in locality order (bit-identical results), inside the timed call
     chis = torch.from_numpy(pts[lo:hi]).to(dev)
     n = hi - lo
     out = (torch.empty(n, dtype=torch.float64, device=dev), torch.empty(n, 2, dtype=torch.float64, device=dev),
@@ -430,6 +432,7 @@ def main():
     if args.path != "auto":
         prob.set_path({"generic": _native.QTET_PATH_GENERIC, "split": _native.QTET_PATH_SPLIT, "direct": _native.QTET_PATH_DIRECT}[args.path])
     path_name = _native.PATH_NAMES[prob.get_path()]
+    prob.set_locality_sort(w["kind"] == "random")      # random workloads: locality order inside the timed call (bit-identical results)
     if args.points and w["kind"] == "random" and args.points != w["B"]:
         # BASELINE's full sizes (config 3: 2^18 dimer N=100 points, config 4: 2^20 trimer N=10 points) are reached this way
         w = dict(w, B=args.points, label=w["label"].replace("2^14", str(args.points)).replace("2^16", str(args.points)))
@@ -594,7 +597,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": w["label"], "points_per_gpu": B, "fock_dim": d, "timesteps": const["timesteps"],
-                           "target_site": "acceptor", "kernel_path": path_name,
+                           "target_site": "acceptor", "kernel_path": path_name, "locality_sort": bool(w["kind"] == "random"),
                            "l2": "256 MiB buffer written between timed iterations (L2 flush)"},
                 "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary, "solver": solver, "config3": config3,
                 "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(B * f * 8),

@@ -77,6 +77,15 @@ int qtet_hamiltonian_host(qtet_problem* p, const double* chis_host, double* H_ho
  */
 int qtet_problem_reserve(qtet_problem* p, int64_t B);
 
+/*
+ * Evaluate the batches of qtet_loss_grad (device-pointer entry point, B >= 4096) in LOCALITY order: the points are ordered by a
+ * coarse 2-D binning of (first, last) parameter on the device, evaluated, and the results scattered back to the caller's order.
+ * A warp of the kernels holds consecutive points and costs what its most expensive point costs, so unordered (random) batches
+ * -- the reference's 'bins' initial guesses, solver_mp.py:17-84 -- run ~20 % faster this way; every result is bit-identical to the
+ * unordered call.  Off by default (grid sweeps are ordered already); qtet_adam_run always orders its live list.
+ */
+int qtet_set_locality_sort(qtet_problem* p, int on);
+
 /* Choose the kernel family (QTET_PATH_*); QTET_EUNSUPPORTED if the problem is not eligible. */
 int qtet_set_path(qtet_problem* p, int path);
 /* Which family the next call will use (QTET_PATH_GENERIC, QTET_PATH_SPLIT or QTET_PATH_DIRECT). */

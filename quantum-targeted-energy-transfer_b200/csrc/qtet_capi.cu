@@ -36,6 +36,7 @@ static void enumerate_states(int N, int f, std::vector<int>& cur, int k, int rem
 int ensure_scratch(qtet_problem* p, size_t bytes) {
     if (bytes <= p->scratch_bytes) return QTET_OK;
     if (p->scratch) cudaFree(p->scratch);
+    if (p->sort_ws) cudaFree(p->sort_ws);
     p->scratch = nullptr;
     p->scratch_bytes = 0;
     size_t want = bytes + bytes / 4 + 4096;
@@ -266,7 +267,42 @@ int qtet_loss_grad(qtet_problem* p, const double* chis_dev, int64_t B, int targe
     if (B == 0) return QTET_OK;
     if (!loss_dev) { set_error("loss is NULL"); return QTET_EINVAL; }
     QTET_ON_DEVICE(p->device);
-    return loss_grad_dispatch(p, chis_dev, B, target_site, loss_dev, grad_dev, tstar_dev, nullptr, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!p->locality_sort || B < 4096)
+        return loss_grad_dispatch(p, chis_dev, B, target_site, loss_dev, grad_dev, tstar_dev, nullptr, st);
+    // Locality order: warps of the kernels hold consecutive points of the batch and cost what their most expensive point costs, so
+    // unordered (random) batches run ~20 % below grid-ordered ones.  Order by a coarse binning, evaluate, scatter back -- every
+    // result is bit-identical to the unordered call (batch invariance).
+    const size_t f = p->f;
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t o_order = 0, o_keys = o_order + al(B * 4), o_hist = o_keys + al(B * 4), o_mm = o_hist + al(65536 * 4),
+                 o_xs = o_mm + 256, o_loss = o_xs + al(B * f * 8), o_grad = o_loss + al(B * 8), o_ts = o_grad + al(B * f * 8),
+                 total = o_ts + al(B * 4);
+    if (total > p->sort_bytes) {
+        if (p->sort_ws) { cudaDeviceSynchronize(); cudaFree(p->sort_ws); }
+        p->sort_ws = nullptr; p->sort_bytes = 0;
+        if (cudaMalloc(&p->sort_ws, total) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(locality-sort buffers) failed"); return QTET_ENOMEM; }
+        p->sort_bytes = total;
+    }
+    char* w = (char*)p->sort_ws;
+    int* order = (int*)(w + o_order);
+    double* xs = (double*)(w + o_xs);
+    double* loss_s = (double*)(w + o_loss);
+    double* grad_s = grad_dev ? (double*)(w + o_grad) : nullptr;
+    int* ts_s = tstar_dev ? (int*)(w + o_ts) : nullptr;
+    rc = launch_locality_order(chis_dev, B, (int)f, order, (int*)(w + o_keys), (int*)(w + o_hist), (unsigned long long*)(w + o_mm), st);
+    if (rc) return rc;
+    rc = launch_sort_gather(order, B, (int)f, chis_dev, xs, st);
+    if (rc) return rc;
+    rc = loss_grad_dispatch(p, xs, B, target_site, loss_s, grad_s, ts_s, nullptr, st);
+    if (rc) return rc;
+    return launch_sort_scatter(order, B, (int)f, loss_s, grad_s, ts_s, loss_dev, grad_dev, tstar_dev, st);
+}
+
+int qtet_set_locality_sort(qtet_problem* p, int on) {
+    if (!p) { set_error("null handle"); return QTET_EINVAL; }
+    p->locality_sort = on ? 1 : 0;
+    return QTET_OK;
 }
 
 int qtet_trace(qtet_problem* p, const double* chis_dev, int64_t B, int target_site, double* trace_dev, void* stream) {

@@ -126,6 +126,11 @@ int launch_big_direct(const ProblemView& pv, BigWorkspace** ws, const double* ch
                       const ChunkHook* hook = nullptr);
 
 int launch_argmin(const double* v, int64_t B, double* min_out, int64_t* idx_out, cudaStream_t st);
+// locality order of a batch (qtet_adam.cu): coarse 2-D binning of the points, results scattered back to the caller's order
+int launch_locality_order(const double* x, int64_t B, int f, int* order, int* keys, int* hist, unsigned long long* mm, cudaStream_t st);
+int launch_sort_gather(const int* order, int64_t B, int f, const double* x, double* xs, cudaStream_t st);
+int launch_sort_scatter(const int* order, int64_t B, int f, const double* loss_s, const double* grad_s, const int* ts_s,
+                        double* loss, double* grad, int* ts, cudaStream_t st);
 
 struct AdamState;        // per-guess optimiser state on the device (qtet_adam.cu)
 
@@ -146,6 +151,10 @@ struct qtet_problem {
     // scratch for *_host convenience calls and the optimiser
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    // qtet_set_locality_sort: evaluate batches in locality order (own buffers: the optimiser's scratch stays untouched)
+    int locality_sort = 0;
+    void* sort_ws = nullptr;
+    size_t sort_bytes = 0;
     // copy/compute pipeline of qtet_loss_grad_host: H2D, kernels and D2H of consecutive slices overlap
     static constexpr int kMaxSlices = 64;
     cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;

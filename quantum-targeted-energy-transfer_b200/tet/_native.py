@@ -41,6 +41,7 @@ def _load():
         "qtet_hamiltonian_host": (C.c_int, [P, D, D]),
         "qtet_problem_reserve": (C.c_int, [P, C.c_int64]),
         "qtet_set_path": (C.c_int, [P, C.c_int]),
+        "qtet_set_locality_sort": (C.c_int, [P, C.c_int]),
         "qtet_get_path": (C.c_int, [P]),
         "qtet_loss_grad": (C.c_int, [P, P, C.c_int64, C.c_int, P, P, P, P]),
         "qtet_loss_grad_host": (C.c_int, [P, P, C.c_int64, C.c_int, P, P, P]),
@@ -66,7 +67,7 @@ def _load():
 
 lib = _load()
 EXPORTS = ["qtet_problem_create", "qtet_problem_destroy", "qtet_problem_dim", "qtet_problem_states",
-           "qtet_problem_time_grid", "qtet_hamiltonian_host", "qtet_problem_reserve", "qtet_set_path", "qtet_get_path",
+           "qtet_problem_time_grid", "qtet_hamiltonian_host", "qtet_problem_reserve", "qtet_set_path", "qtet_set_locality_sort", "qtet_get_path",
            "qtet_loss_grad", "qtet_loss_grad_host", "qtet_trace", "qtet_adam_run", "qtet_argmin",
            "qtet_fp64_peak", "qtet_fp64_peak2", "qtet_profile_enable", "qtet_profile_read", "qtet_stats", "qtet_launch_count", "qtet_last_error",
            "qtet_version"]
@@ -188,6 +189,10 @@ class Problem:
     def reserve(self, batch: int):
         """Size the workspaces for batches of up to `batch` points now (no allocation / synchronisation in later calls)."""
         _check(lib.qtet_problem_reserve(self._h, int(batch)), "qtet_problem_reserve")
+
+    def set_locality_sort(self, on: bool = True):
+        """Evaluate loss_grad batches (device tensors, B >= 4096) in locality order; results are bit-identical, random batches ~20 % faster."""
+        _check(lib.qtet_set_locality_sort(self._h, 1 if on else 0), "qtet_set_locality_sort")
 
     def set_path(self, path: int):
         _check(lib.qtet_set_path(self._h, int(path)), "qtet_set_path")

@@ -294,3 +294,24 @@ def test_handles_of_different_sizes_interleaved(native, O):
         small.close()
     assert np.abs(L0 - O.loss_grad_batch(make_const(20), X, 1)[0]).max() < 1e-10 * 20
     big.close()
+
+
+@pytest.mark.parametrize("N,omegas", [(20, (-3, 3)), (40, (-3, 3)), (4, (-3, 3, 3)), (10, (-3, 3, 3))])
+def test_locality_sort_is_bit_identical(native, N, omegas):
+    """qtet_set_locality_sort: the batch is evaluated in a device-side locality order and scattered back -- same bits as the
+    plain call on every path (it relies on, and therefore also tests, batch invariance), ragged sizes included."""
+    import torch
+    f = len(omegas)
+    X = np.random.default_rng(33).uniform(-10, 10, (20011, f))
+    X[5] = X[77]                                              # duplicates share a bin
+    p = native.Problem.from_const(make_const(N, omegas))
+    ref = [t.cpu().numpy() for t in p.loss_grad(X, f - 1)]
+    p.set_locality_sort(True)
+    got = [t.cpu().numpy() for t in p.loss_grad(X, f - 1)]
+    small = [t.cpu().numpy() for t in p.loss_grad(X[:1000], f - 1)]        # below the threshold: plain path
+    p.set_locality_sort(False)
+    for a, b in zip(ref, got):
+        assert np.array_equal(a, b)
+    for a, b in zip(ref, small):
+        assert np.array_equal(a[:1000], b)
+    p.close()
