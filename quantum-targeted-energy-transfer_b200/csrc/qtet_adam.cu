@@ -467,7 +467,9 @@ extern "C" int qtet_adam_run(qtet_problem* p, double* chis_dev, int64_t B, int t
             QTET_CUDA(cudaStreamWaitEvent(p->s_poll, p->ev_cnt[slot], 0));
             QTET_CUDA(cudaMemcpyAsync(p->h_poll + slot, cnt + cur, sizeof(int), cudaMemcpyDeviceToHost, p->s_poll));
             QTET_CUDA(cudaEventRecord(p->ev_poll[slot], p->s_poll));
-            if (sort_on && epoch % resort == 0) {
+            // (only while many guesses are alive: with a small list an epoch is a latency chain per kernel, and the six extra launches
+            // cost more than the ordering saves -- 12 500 guesses per GPU: 0.205 s without, 0.223 s with)
+            if (sort_on && epoch % resort == 0 && n_bound >= 32768) {
                 const unsigned gN = (unsigned)((n_bound + TPB - 1) / TPB);
                 QTET_CUDA(cudaMemcpyAsync(mm, mm0, sizeof(mm0), cudaMemcpyHostToDevice, st));
                 QTET_CUDA(cudaMemsetAsync(hist, 0, (size_t)nb * nb * sizeof(int), st));
