@@ -239,15 +239,31 @@ int qtet_set_path(qtet_problem* p, int path) {
 
 int qtet_get_path(const qtet_problem* p) { return p ? p->path : QTET_EINVAL; }
 
+// buffers of the locality-ordered qtet_loss_grad (order, keys, histogram, gathered inputs, ordered outputs)
+static size_t sort_ws_bytes(int64_t B, size_t f) {
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    return 2 * al((size_t)B * 4) + al(65536 * 4) + 256 + 2 * al((size_t)B * f * 8) + al((size_t)B * 8) + al((size_t)B * 4);
+}
+static int ensure_sort_ws(qtet_problem* p, int64_t B) {
+    const size_t total = sort_ws_bytes(B, (size_t)p->f);
+    if (total <= p->sort_bytes) return QTET_OK;
+    if (p->sort_ws) { cudaDeviceSynchronize(); cudaFree(p->sort_ws); }
+    p->sort_ws = nullptr; p->sort_bytes = 0;
+    if (cudaMalloc(&p->sort_ws, total) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(locality-sort buffers) failed"); return QTET_ENOMEM; }
+    p->sort_bytes = total;
+    return QTET_OK;
+}
+
 int qtet_problem_reserve(qtet_problem* p, int64_t B) {
     if (!p || B < 0) { set_error("bad argument"); return QTET_EINVAL; }
     QTET_ON_DEVICE(p->device);
     const size_t f = p->f;
     // scratch of the *_host entry point and of the optimiser (the larger of the two layouts)
     const size_t host_call = (size_t)B * (2 * f + 1) * 8 + (size_t)B * 4 + 64;
-    const size_t adam = (size_t)B * (5 * f * 8 + 3 * 8 + f * 4 + 4 * 4) + 16 * 256;
+    const size_t adam = (size_t)B * (f * 52 + 24 + 28) + 65536 * 4 + 32 * 256;        // qtet_adam_run's layout incl. the re-ordering buffers
     int rc = ensure_scratch(p, host_call > adam ? host_call : adam);
     if (rc) return rc;
+    if (p->locality_sort && B >= 4096) { rc = ensure_sort_ws(p, B); if (rc) return rc; }
     if (p->path == QTET_PATH_DIRECT && direct_eligible(p->view)) return direct_reserve(p->view, &p->direct_ws, B, B <= (1LL << 22));
     return QTET_OK;
 }
@@ -276,14 +292,9 @@ int qtet_loss_grad(qtet_problem* p, const double* chis_dev, int64_t B, int targe
     const size_t f = p->f;
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     const size_t o_order = 0, o_keys = o_order + al(B * 4), o_hist = o_keys + al(B * 4), o_mm = o_hist + al(65536 * 4),
-                 o_xs = o_mm + 256, o_loss = o_xs + al(B * f * 8), o_grad = o_loss + al(B * 8), o_ts = o_grad + al(B * f * 8),
-                 total = o_ts + al(B * 4);
-    if (total > p->sort_bytes) {
-        if (p->sort_ws) { cudaDeviceSynchronize(); cudaFree(p->sort_ws); }
-        p->sort_ws = nullptr; p->sort_bytes = 0;
-        if (cudaMalloc(&p->sort_ws, total) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(locality-sort buffers) failed"); return QTET_ENOMEM; }
-        p->sort_bytes = total;
-    }
+                 o_xs = o_mm + 256, o_loss = o_xs + al(B * f * 8), o_grad = o_loss + al(B * 8), o_ts = o_grad + al(B * f * 8);
+    rc = ensure_sort_ws(p, B);          // (sized by qtet_problem_reserve if the option was set before it)
+    if (rc) return rc;
     char* w = (char*)p->sort_ws;
     int* order = (int*)(w + o_order);
     double* xs = (double*)(w + o_xs);
